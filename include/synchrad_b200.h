@@ -1,0 +1,142 @@
+/* synchrad_b200 — C ABI of the B200 spectral-integration path (libsynchrad_b200.so).
+ *
+ * The reference (hightower8083/synchrad) has no FFI: its device boundary is the positional
+ * argument list that `SynchRad._process_track` marshals into the PyOpenCL kernels, ONE PARTICLE
+ * PER LAUNCH (synchrad/calc.py:292-353; kernel prototypes kernel_farfield.cl:6-28,
+ * kernel_nearfield.cl:5-27).  This header is that argument list turned into a batched C ABI:
+ * the same tables, the same per-track scalars, all particles of a rank in one call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller (torch,
+ *     cudaMalloc, ...) owns every buffer, the library allocates nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous
+ *     with respect to the host unless stated;
+ *   - spectra are ACCUMULATED INTO (`+=`), like the reference kernels' `spectrum[...] +=`
+ *     (kernel_farfield.cl:102); zeroing is the caller's job (calc.py:482-484);
+ *   - spectra are float64 in the reference's device layout (nSnaps, nPhi, nAxis2, nOmega)
+ *     (calc.py:455), whatever the compute dtype (documented deviation from Q5: the
+ *     cross-particle sum is carried in fp64, the host result is fp64 anyway, calc.py:576-577);
+ *   - return value 0 = success, <0 = error; the message is in srb_last_error() (thread-local).
+ *     No C++ exception crosses this boundary.
+ */
+#ifndef SYNCHRAD_B200_H
+#define SYNCHRAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRB_ABI_VERSION 1
+
+/* mode: which kernel file of the reference is replaced (calc.py:617-620) */
+#define SRB_MODE_FAR 0  /* kernel_farfield.cl  */
+#define SRB_MODE_NEAR 1 /* kernel_nearfield.cl */
+
+/* comp: which __kernel of that file (dispatch of calc.py:324-353) */
+#define SRB_COMP_TOTAL 0             /* total                    -> 1 spectrum  */
+#define SRB_COMP_CARTESIAN 1         /* cartesian_comps          -> 3 spectra   */
+#define SRB_COMP_CARTESIAN_COMPLEX 2 /* cartesian_comps_complex  -> 6 spectra   */
+#define SRB_COMP_SPHERIC 3           /* spheric_comps (far only) -> 3 spectra   */
+#define SRB_COMP_SPHERIC_COMPLEX 4   /* spheric_comps_complex    -> 6 spectra   */
+
+/* dtype: the Mako variable `my_dtype` (calc.py:610-611) */
+#define SRB_DTYPE_F64 0
+#define SRB_DTYPE_F32 1
+
+/* phasor: how exp(i*omega*tau) is evaluated per node */
+#define SRB_PHASOR_AUTO 0   /* recurrence when omega_uniform, else direct */
+#define SRB_PHASOR_DIRECT 1 /* per-node sincos of the reference's rounded phase */
+#define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
+
+/* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
+ * Tables are in the compute dtype, exactly as `_init_data` uploads them (calc.py:486-512):
+ * omega is already multiplied by 2*pi. */
+typedef struct srb_grid {
+  int32_t mode;    /* SRB_MODE_*  */
+  int32_t comp;    /* SRB_COMP_*  */
+  int32_t dtype;   /* SRB_DTYPE_* */
+  int32_t native;  /* `f_native` (calc.py:612-615); honoured for F32 + direct phasor only (Q9) */
+  int32_t phasor;  /* SRB_PHASOR_* */
+  int32_t omega_uniform; /* host hint: table is an ascending uniform grid (no Features) */
+  uint32_t nOmega, nAxis2, nPhi; /* `gridNodeNums`; nAxis2 = nTheta (far) | nRadius (near) */
+  uint32_t nSnaps;
+  const void* omega;      /* [nOmega]  2*pi*omega            */
+  const void* sinTheta;   /* [nAxis2]  far                   */
+  const void* cosTheta;   /* [nAxis2]  far                   */
+  const void* radius;     /* [nAxis2]  near                  */
+  const void* sinPhi;     /* [nPhi]                          */
+  const void* cosPhi;     /* [nPhi]                          */
+  const void* formFactor; /* [nOmega] or NULL; applied by far cartesian_complex only,
+                             as in the reference (kernel_farfield.cl:271,324-325) */
+  double L_screen;        /* near: `distanceToScreen`        */
+  double dt;              /* `timeStep`, already rounded to the compute dtype */
+  double omega_first_host, omega_last_host; /* host copies of omega[0], omega[nOmega-1] */
+} srb_grid;
+
+/* All tracks of this rank, SoA and concatenated: the `args_track` of calc.py:306-307 for
+ * every particle at once.  Track t occupies [offsets[t], offsets[t+1]) of each coordinate array. */
+typedef struct srb_tracks {
+  uint32_t nTracks;
+  const void *x, *y, *z, *ux, *uy, *uz; /* compute dtype */
+  const uint64_t* offsets;              /* [nTracks+1] */
+  const void* w;                        /* [nTracks] compute dtype: `wp` */
+  const uint32_t* itStart;              /* [nTracks] */
+  const uint32_t* itEnd;                /* [nTracks] `np.uint32(it_range[-1])` (calc.py:307) */
+  const uint32_t* itSnaps;              /* snapshot iterations (calc.py:626-630) */
+  uint32_t itSnapsStride;               /* 0: one [nSnaps] table shared by all tracks;
+                                           nSnaps: per-track rows (it_range=None, calc.py:297-301) */
+  uint64_t totalSteps_host;             /* host copy of offsets[nTracks] (work partitioning) */
+} srb_tracks;
+
+/* Statistics of the last srb_integrate on this stream (device memory, 2 x uint64):
+ * [0] (node,step) updates that passed the Nyquist guard, [1] updates visited. */
+
+int srb_version(void);
+const char* srb_last_error(void);
+
+/* Number of spectra `comp` produces in `mode` (1, 3 or 6); <0 if the combination does not
+ * exist (the reference has no near-field spheric kernels, calc.py:342 would raise). */
+int srb_num_spectra(int mode, int comp);
+
+/* Bytes of scratch srb_integrate wants for this problem (private partial spectra of the
+ * particle chunks).  Never fails for valid inputs; 0 is possible. */
+size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks);
+
+/* The hot path: replaces the whole `for itr in calc_iterator: ... _process_track` loop of
+ * calc.py:257-267 and the kernels it launches.
+ *   spectra[n_spectra] : float64 device buffers, each nSnaps*nPhi*nAxis2*nOmega, `+=`
+ *   scratch            : device buffer of >= srb_scratch_bytes() (may be NULL if that is 0);
+ *                        a smaller buffer is accepted and only reduces parallelism
+ *   counters           : device uint64[2] or NULL; zeroed and filled by the call */
+int srb_integrate(const srb_grid* grid, const srb_tracks* tracks, double* const* spectra,
+                  int n_spectra, void* scratch, size_t scratch_bytes, uint64_t* counters,
+                  void* stream);
+
+/* Same computation through HOST buffers (all pointers of grid/tracks/spectra are host
+ * pointers here): uploads, integrates, downloads and adds into the host spectra.
+ * Synchronous.  This is the entry a non-Python host would bind. */
+int srb_integrate_host(const srb_grid* grid, const srb_tracks* tracks, double* const* spectra,
+                       int n_spectra, uint64_t* counters_host, int device);
+
+/* Replaces `_spectr_from_device` + `_gather_result_mpi` plumbing on the device side
+ * (calc.py:560-577): dst[nSnaps][nOmega][nAxis2][nPhi] = swapaxes(src,-1,-3). */
+int srb_swap_axes(const double* src, double* dst, uint32_t nSnaps, uint32_t nOmega,
+                  uint32_t nAxis2, uint32_t nPhi, void* stream);
+
+/* How the last srb_integrate was configured (for benchmarks/diagnostics). */
+typedef struct srb_launch_info {
+  int32_t kind;        /* 0 direct, 1 recurrence */
+  int32_t tile_width;  /* omega nodes per thread */
+  uint32_t chunk_nodes, n_chunks, n_virtual_dirs, n_particle_chunks;
+  uint32_t grid_blocks, block_threads, smem_bytes;
+  uint32_t kernels_launched;
+} srb_launch_info;
+int srb_last_launch(srb_launch_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNCHRAD_B200_H */

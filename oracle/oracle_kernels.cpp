@@ -1,0 +1,260 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// CPU restatement of the reference's spectral-integration kernels, one logical work-item per
+// grid node, one call per particle (exactly the reference launch granularity, calc.py:257-267).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library, and only as the checker / CPU baseline.
+//
+// What is restated (file:line relative to /root/reference/synchrad/):
+//   far-field loop skeleton ............ kernel_farfield.cl:30-108   (shared by all 5 far kernels)
+//   far epilogues ....................... total :100-106, cartesian :208-222, cartesian_complex
+//                                         :329-341, spheric :452-466, spheric_complex :581-592
+//   spheric projection .................. kernel_farfield.cl:385-388,442-445
+//   FormFactor (far cartesian_complex) .. kernel_farfield.cl:271,324-325
+//   near-field loop ..................... kernel_nearfield.cl:29-103 (+ epilogues :197-211, :311-323)
+//
+// Arithmetic policy ("strict" build, the parity oracle): no FMA contraction
+// (-ffp-contract=off), OpenCL dot(a,b) on 3-vectors restated as ((a0*b0 + a1*b1) + a2*b2),
+// rsqrt(x) restated as 1/sqrt(x), sin/cos from libm in the compute type, M_PI cast to the
+// compute type.  OpenCL leaves contraction and the ulp error of rsqrt/sin/cos
+// implementation-defined, so the reference has no single bit-exact answer;
+// this file fixes one.
+//
+// PARITY PIN: the reference stores no golden vectors and its OpenCL path cannot run in this
+// image (no pyopencl / pocl).  This oracle is pinned (tests/test_oracle_golden.py) against
+//   (1) the reference's own known-answer criterion, the analytic undulator energy of
+//       tests/test_undulator_analytic.py:78-87 and tests/test_undulator_analytic_near.py:81-90,
+//   (2) the spot values of BASELINE.md §2 (an independent NumPy restatement made during the
+//       survey), and (3) an independent vectorised NumPy restatement in oracle/numpy_oracle.py.
+// Bit-level parity with "the" OpenCL result is therefore UNPINNED (no such result exists here).
+//
+// Compute types: 0 = double, 1 = float, 2 = long double ("truth": same double-rounded inputs,
+// 80-bit arithmetic; inputs/outputs are double arrays).
+
+#include <cmath>
+#include <cstdint>
+#include <cstddef>
+
+namespace {
+
+template <typename T> struct V3 { T a, b, c; };
+
+template <typename T> inline T dot3(const V3<T>& p, const V3<T>& q) {
+  return (p.a * q.a + p.b * q.b) + p.c * q.c;
+}
+template <typename T> inline V3<T> operator*(T s, const V3<T>& v) { return {s * v.a, s * v.b, s * v.c}; }
+template <typename T> inline V3<T> operator*(const V3<T>& v, T s) { return {v.a * s, v.b * s, v.c * s}; }
+template <typename T> inline V3<T> operator+(const V3<T>& p, const V3<T>& q) { return {p.a + q.a, p.b + q.b, p.c + q.c}; }
+template <typename T> inline V3<T> operator-(const V3<T>& p, const V3<T>& q) { return {p.a - q.a, p.b - q.b, p.c - q.c}; }
+template <typename T> inline V3<T> operator-(const V3<T>& p) { return {-p.a, -p.b, -p.c}; }
+
+inline float o_sin(float x) { return sinf(x); }
+inline float o_cos(float x) { return cosf(x); }
+inline float o_sqrt(float x) { return sqrtf(x); }
+inline float o_abs(float x) { return fabsf(x); }
+inline double o_sin(double x) { return sin(x); }
+inline double o_cos(double x) { return cos(x); }
+inline double o_sqrt(double x) { return sqrt(x); }
+inline double o_abs(double x) { return fabs(x); }
+inline long double o_sin(long double x) { return sinl(x); }
+inline long double o_cos(long double x) { return cosl(x); }
+inline long double o_sqrt(long double x) { return sqrtl(x); }
+inline long double o_abs(long double x) { return fabsl(x); }
+template <typename T> inline T o_rsqrt(T x) { return T(1) / o_sqrt(x); }
+
+// comp codes (same numbering as include/synchrad_b200.h)
+enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
+
+struct Common {
+  const void *x, *y, *z, *ux, *uy, *uz;
+  double wp;
+  uint32_t itStart, itEnd, nSteps;
+  const void* omega;       // already 2*pi*omega in compute dtype (calc.py:494-495)
+  const void* axisA;       // far: sinTheta ; near: radius
+  const void* axisB;       // far: cosTheta ; near: unused
+  const void* sinPhi;
+  const void* cosPhi;
+  double L_screen;         // near only
+  uint32_t nOmega, nAxis2, nPhi;
+  double dt;
+  uint32_t nSnaps;
+  const uint32_t* itSnaps;
+  const void* formFactor;  // may be null
+};
+
+// S = storage type of the arrays, T = compute type
+template <typename S, typename T, bool NEAR>
+void run_particle(int comp, void* const* spectra, const Common& a, long long* passed) {
+  const S* x = (const S*)a.x; const S* y = (const S*)a.y; const S* z = (const S*)a.z;
+  const S* ux = (const S*)a.ux; const S* uy = (const S*)a.uy; const S* uz = (const S*)a.uz;
+  const S* omega = (const S*)a.omega; const S* axA = (const S*)a.axisA; const S* axB = (const S*)a.axisB;
+  const S* sinPhi = (const S*)a.sinPhi; const S* cosPhi = (const S*)a.cosPhi;
+  const S* FF = (const S*)a.formFactor;
+  const uint32_t nOmega = a.nOmega, nA2 = a.nAxis2, nPhi = a.nPhi;
+  const uint32_t nTotal = nA2 * nPhi * nOmega;
+  const T wp = (T)(S)a.wp;
+  const T dt = (T)(S)a.dt;
+  const T distanceToScreen = (T)(S)a.L_screen;
+  const T PI = (T)M_PI;
+  const bool cplx = (comp == COMP_CART_CPLX || comp == COMP_SPH_CPLX);
+  const bool sph = (comp == COMP_SPH || comp == COMP_SPH_CPLX);
+  long long npass = 0;
+
+#pragma omp parallel for schedule(static) reduction(+ : npass)
+  for (uint32_t gti = 0; gti < nTotal; gti++) {
+    const uint32_t iPhi = gti / (nOmega * nA2);
+    const uint32_t iA2 = (gti - iPhi * nOmega * nA2) / nOmega;
+    const uint32_t iOmega = gti - iPhi * nOmega * nA2 - iA2 * nOmega;
+
+    const T omegaLocal = (T)omega[iOmega];
+    V3<T> nVec{}, thVec{}, phVec{}, coordOnScreen{};
+    if (!NEAR) {
+      const T sT = (T)axA[iA2], cT = (T)axB[iA2], sP = (T)sinPhi[iPhi], cP = (T)cosPhi[iPhi];
+      nVec = {sT * cP, sT * sP, cT};
+      thVec = {cT * cP, cT * sP, -sT};
+      phVec = {-sP, cP, T(0)};
+    } else {
+      const T r = (T)axA[iA2], sP = (T)sinPhi[iPhi], cP = (T)cosPhi[iPhi];
+      coordOnScreen = {r * cP, r * sP, distanceToScreen};
+    }
+    // far cartesian_complex is the only kernel that applies the form factor
+    // (kernel_farfield.cl:271,324-325; declared-but-unused elsewhere)
+    const bool useFF = (!NEAR && comp == COMP_CART_CPLX);
+    const T FormFactorLocal = (useFF && FF) ? (T)FF[iOmega] : T(1);
+
+    const T dtInv = T(1) / dt;
+    const T wpdt2 = wp * dt * dt;
+    const T wpdt = o_sqrt(wp) * dt;
+    T phasePrev = T(0);
+    V3<T> Re{T(0), T(0), T(0)}, Im{T(0), T(0), T(0)};
+
+    uint32_t iSnap;
+    for (iSnap = 0; iSnap < a.nSnaps; iSnap++)
+      if (a.itStart < a.itSnaps[iSnap]) break;
+
+    // NB uint wrap-around of itEnd-1 / nSteps-1 is not reproduced: itEnd==0 or nSteps==0 do nothing
+    const uint32_t loopEnd = a.itEnd > 0 ? a.itEnd - 1 : 0;
+    for (uint32_t it = 0; it < loopEnd; it++) {
+      const uint32_t it_glob = a.itStart + it;
+      if (a.nSteps > 0 && it < a.nSteps - 1) {
+        const T time = (T)it_glob * dt;
+        const V3<T> xLocal{(T)x[it], (T)y[it], (T)z[it]};
+        if (!NEAR) {
+          const T phase = omegaLocal * (time - dot3(xLocal, nVec));
+          const T dPhase = o_abs(phase - phasePrev);
+          phasePrev = phase;
+          if (dPhase < PI) {
+            npass++;
+            V3<T> uLocal{(T)ux[it], (T)uy[it], (T)uz[it]};
+            V3<T> uNext{(T)ux[it + 1], (T)uy[it + 1], (T)uz[it + 1]};
+            T gammaInv = o_rsqrt(T(1) + dot3(uLocal, uLocal));
+            uLocal = uLocal * gammaInv;
+            gammaInv = o_rsqrt(T(1) + dot3(uNext, uNext));
+            uNext = uNext * gammaInv;
+            const V3<T> aLocal = (uNext - uLocal) * dtInv;
+            uLocal = T(0.5) * (uNext + uLocal);
+            T c1 = dot3(aLocal, nVec);
+            T c2 = T(1) - dot3(uLocal, nVec);
+            c2 = T(1) / c2;
+            c1 = c1 * c2 * c2;
+            const T sinPhase = o_sin(phase);
+            const T cosPhase = o_cos(phase);
+            V3<T> amplitude = c1 * (nVec - uLocal) - c2 * aLocal;
+            if (sph) {
+              V3<T> s{dot3(nVec, amplitude), dot3(thVec, amplitude), dot3(phVec, amplitude)};
+              amplitude = s;
+            }
+            if (useFF) {
+              Re = Re + (amplitude * cosPhase) * FormFactorLocal;
+              Im = Im + (amplitude * sinPhase) * FormFactorLocal;
+            } else {
+              Re = Re + amplitude * cosPhase;
+              Im = Im + amplitude * sinPhase;
+            }
+          }
+        } else {
+          const V3<T> rVec = coordOnScreen - xLocal;
+          const T rLocal = o_sqrt(dot3(rVec, rVec));
+          const T phase = omegaLocal * (time + rLocal);
+          const T dPhase = o_abs(phase - phasePrev);
+          phasePrev = phase;
+          if (dPhase < PI) {
+            npass++;
+            const T rInv = T(1) / rLocal;
+            const V3<T> nV = rInv * rVec;
+            V3<T> uLocal{(T)ux[it], (T)uy[it], (T)uz[it]};
+            const T gammaInv = o_rsqrt(T(1) + dot3(uLocal, uLocal));
+            uLocal = uLocal * gammaInv;
+            const T sinPhase = o_sin(phase);
+            const T cosPhase = o_cos(phase);
+            const V3<T> c1 = (omegaLocal * rInv) * (uLocal - nV);
+            const V3<T> c2 = (rInv * rInv) * nV;
+            Re = Re + ((-c1) * sinPhase + c2 * cosPhase);
+            Im = Im + (c1 * cosPhase + c2 * sinPhase);
+          }
+        }
+      }
+      // Q4: the reference reads itSnaps[nSnaps] out of bounds here; outcome restated (no flush)
+      if (iSnap < a.nSnaps && it_glob + 2 == a.itSnaps[iSnap]) {
+        const size_t o = (size_t)gti + (size_t)nTotal * iSnap;
+        if (!cplx) {
+          if (comp == COMP_TOTAL) {
+            S* s0 = (S*)spectra[0];
+            s0[o] = (S)((T)s0[o] + wpdt2 * (dot3(Re, Re) + dot3(Im, Im)));
+          } else {
+            S* s0 = (S*)spectra[0]; S* s1 = (S*)spectra[1]; S* s2 = (S*)spectra[2];
+            s0[o] = (S)((T)s0[o] + wpdt2 * (Re.a * Re.a + Im.a * Im.a));
+            s1[o] = (S)((T)s1[o] + wpdt2 * (Re.b * Re.b + Im.b * Im.b));
+            s2[o] = (S)((T)s2[o] + wpdt2 * (Re.c * Re.c + Im.c * Im.c));
+          }
+        } else {
+          S* q[6]; for (int k = 0; k < 6; k++) q[k] = (S*)spectra[k];
+          q[0][o] = (S)((T)q[0][o] + wpdt * Re.a); q[1][o] = (S)((T)q[1][o] + wpdt * Im.a);
+          q[2][o] = (S)((T)q[2][o] + wpdt * Re.b); q[3][o] = (S)((T)q[3][o] + wpdt * Im.b);
+          q[4][o] = (S)((T)q[4][o] + wpdt * Re.c); q[5][o] = (S)((T)q[5][o] + wpdt * Im.c);
+        }
+        iSnap += 1;
+      }
+    }
+  }
+  if (passed) *passed += npass;
+}
+
+}  // namespace
+
+extern "C" {
+
+// One reference kernel launch (one particle).  mode: 0 far, 1 near.  ctype: 0 double,
+// 1 float, 2 long double (arrays are double).  Returns 0, or -1 on a bad code.
+// `passed` (optional) accumulates the number of (node, step) updates that passed the
+// Nyquist guard (kernel_farfield.cl:72).
+int srb_oracle_particle(int mode, int comp, int ctype, void* const* spectra,
+                        const void* x, const void* y, const void* z,
+                        const void* ux, const void* uy, const void* uz,
+                        double wp, uint32_t itStart, uint32_t itEnd, uint32_t nSteps,
+                        const void* omega, const void* axisA, const void* axisB,
+                        const void* sinPhi, const void* cosPhi, double L_screen,
+                        uint32_t nOmega, uint32_t nAxis2, uint32_t nPhi, double dt,
+                        uint32_t nSnaps, const uint32_t* itSnaps, const void* formFactor,
+                        long long* passed) {
+  Common a{x, y, z, ux, uy, uz, wp, itStart, itEnd, nSteps, omega, axisA, axisB, sinPhi, cosPhi,
+           L_screen, nOmega, nAxis2, nPhi, dt, nSnaps, itSnaps, formFactor};
+  if (comp < 0 || comp > 4) return -1;
+  if (mode == 1 && (comp == COMP_SPH || comp == COMP_SPH_CPLX)) return -1;  // no such near kernels
+  if (mode == 0) {
+    if (ctype == 0) run_particle<double, double, false>(comp, spectra, a, passed);
+    else if (ctype == 1) run_particle<float, float, false>(comp, spectra, a, passed);
+    else if (ctype == 2) run_particle<double, long double, false>(comp, spectra, a, passed);
+    else return -1;
+  } else if (mode == 1) {
+    if (ctype == 0) run_particle<double, double, true>(comp, spectra, a, passed);
+    else if (ctype == 1) run_particle<float, float, true>(comp, spectra, a, passed);
+    else if (ctype == 2) run_particle<double, long double, true>(comp, spectra, a, passed);
+    else return -1;
+  } else return -1;
+  return 0;
+}
+
+int srb_oracle_abi(void) { return 1; }
+
+}  // extern "C"

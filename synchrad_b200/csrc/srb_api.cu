@@ -1,0 +1,348 @@
+// synchrad_b200 — __global__ entry points and the C ABI of include/synchrad_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/synchrad_b200.h"
+#include "srb_core.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local srb_launch_info g_info;
+
+int fail(const std::string& m) { g_err = m; return -1; }
+#define SRB_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+  } while (0)
+
+constexpr int NW = 8;   // warps (= virtual directions) per block
+
+template <class C>
+__global__ void __launch_bounds__(NW * 32, 1) k_integrate(const srb::Params P) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const uint32_t warp = threadIdx.x >> 5;
+  srb::WarpSmem<C>* sm = reinterpret_cast<srb::WarpSmem<C>*>(smraw) + warp;
+  const uint32_t nVDtiles = (P.nVD + NW - 1) / NW;
+  const uint32_t vd = (blockIdx.x % nVDtiles) * NW + warp;   // neighbouring blocks share the tracks
+  const uint32_t pc = blockIdx.x / nVDtiles;
+  if (vd >= P.nVD) return;
+  srb::ThreadState<C> st;
+  srb::warp_task<C>(P, vd, pc, *sm, &st);
+}
+
+// out[c][i] += sum over particle chunks of the private partial spectra (fixed order: deterministic)
+__global__ void k_reduce_slabs(srb::Params P, int nOut, size_t perOut) {
+  const size_t n = (size_t)nOut * perOut;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (uint32_t s = 0; s + 1 < P.nPC; s++) acc += P.slabs[(size_t)s * P.slabStride + i];
+    const int c = (int)(i / perOut);
+    P.out[c][i - (size_t)c * perOut] += acc;
+  }
+}
+
+__global__ void k_swap_axes(const double* __restrict__ src, double* __restrict__ dst, uint32_t nSnaps,
+                            uint32_t nO, uint32_t nA, uint32_t nP) {
+  // src (nSnaps, nP, nA, nO) -> dst (nSnaps, nO, nA, nP)
+  const size_t n = (size_t)nSnaps * nO * nA * nP;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t io = (uint32_t)(i % nO); size_t r = i / nO;
+    const uint32_t ia = (uint32_t)(r % nA); r /= nA;
+    const uint32_t ip = (uint32_t)(r % nP); const size_t is = r / nP;
+    dst[((is * nO + io) * nA + ia) * nP + ip] = src[i];
+  }
+}
+
+struct Launcher {
+  void (*kernel)(const srb::Params);
+  size_t smem;
+  int chunk;
+};
+
+template <class C> Launcher make_launcher() {
+  return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK};
+}
+
+using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::MODE_FAR; using srb::MODE_NEAR;
+
+// kind, mode, dtype, native, tile width -> kernel
+bool pick(int kind, int mode, int dtype, bool native, int tw, Launcher* L) {
+#define SRB_CASE(K, M, D, NAT, TWV, TI, TM)                                                   \
+  if (kind == K && mode == M && dtype == D && native == NAT && tw == TWV) {                   \
+    *L = make_launcher<Cfg<TI, TM, M, K, TWV, NAT>>(); return true; }
+  // recurrence, far
+  SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 16, double, double)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 8, double, double)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 4, double, double)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 16, float, float)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 8, float, float)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 4, float, float)
+  // recurrence, near
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 8, double, double)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 4, double, double)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 2, double, double)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 8, float, float)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 4, float, float)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 2, float, float)
+  // direct
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 8, double, double)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 4, double, double)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 2, double, double)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 8, double, double)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 4, double, double)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 2, double, double)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 8, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 4, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 2, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 8, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 4, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 2, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 8, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 4, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, float, float)
+#undef SRB_CASE
+  return false;
+}
+
+struct Plan {
+  int kind, tw;
+  bool native;
+  Launcher L;
+  uint32_t chunkNodes, nChunks, nVD, nVDtiles, nPC;
+  int blocksPerSM, numSM;
+  size_t perOut, slabDoubles;
+  int nOut;
+};
+
+int validate(const srb_grid* g, const srb_tracks* t) {
+  if (!g || !t) return fail("null grid/tracks");
+  if (g->mode != SRB_MODE_FAR && g->mode != SRB_MODE_NEAR) return fail("bad mode");
+  if (srb_num_spectra(g->mode, g->comp) < 0)
+    return fail("no such kernel: comp/mode combination does not exist in the reference");
+  if (g->dtype != SRB_DTYPE_F64 && g->dtype != SRB_DTYPE_F32) return fail("bad dtype");
+  if (g->nOmega == 0 || g->nAxis2 == 0 || g->nPhi == 0) return fail("empty grid");
+  if (g->nSnaps == 0) return fail("nSnaps must be >= 1");
+  if ((uint64_t)g->nOmega * g->nAxis2 * g->nPhi >= (1ull << 32)) return fail("grid too large (uint32 node index, as in the reference)");
+  if (!g->omega || !g->sinPhi || !g->cosPhi) return fail("null grid table");
+  if (g->mode == SRB_MODE_FAR && (!g->sinTheta || !g->cosTheta)) return fail("far mode needs sinTheta/cosTheta");
+  if (g->mode == SRB_MODE_NEAR && !g->radius) return fail("near mode needs radius");
+  if (t->nTracks && (!t->x || !t->y || !t->z || !t->ux || !t->uy || !t->uz || !t->offsets || !t->w ||
+                     !t->itStart || !t->itEnd || !t->itSnaps))
+    return fail("null track array");
+  if (t->itSnapsStride != 0 && t->itSnapsStride != g->nSnaps) return fail("itSnapsStride must be 0 or nSnaps");
+  return 0;
+}
+
+int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool unlimited, Plan* p) {
+  int dev = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&p->numSM, cudaDevAttrMultiProcessorCount, dev));
+  const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
+  if (g->phasor == SRB_PHASOR_RECUR && !uniform) return fail("phasor recurrence needs an ascending uniform omega grid");
+  p->kind = (g->phasor == SRB_PHASOR_DIRECT || !uniform) ? KIND_DIRECT : KIND_RECUR;
+  p->native = (p->kind == KIND_DIRECT && g->dtype == SRB_DTYPE_F32 && g->native != 0);   // Q9
+  const int tiles = p->kind == KIND_RECUR ? 16 : 32;
+  int twMax, twMin;
+  if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
+  else { twMax = 8; twMin = 2; }
+  p->tw = twMax;
+  for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }
+  if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, &p->L)) return fail("internal: no kernel for this configuration");
+  p->chunkNodes = (uint32_t)p->L.chunk;
+  p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;
+  p->nVD = g->nPhi * g->nAxis2 * p->nChunks;
+  p->nVDtiles = (p->nVD + NW - 1) / NW;
+  p->nOut = srb_num_spectra(g->mode, g->comp);
+  p->perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
+  p->slabDoubles = p->perOut * p->nOut;
+  SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->L.smem));
+  SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, NW * 32, p->L.smem));
+  if (p->blocksPerSM < 1) return fail("kernel does not fit on an SM");
+  // particle chunks: fill whole waves of the machine; bounded by tracks, scratch and 64 waves
+  const uint64_t slots = (uint64_t)p->numSM * p->blocksPerSM;
+  uint64_t maxPC = t->nTracks ? t->nTracks : 1;
+  const uint64_t slabCap = unlimited ? (uint64_t)(1ull << 30) / (p->slabDoubles * 8) : scratch_bytes / (p->slabDoubles * 8);
+  maxPC = std::min<uint64_t>(maxPC, 1 + slabCap);
+  maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, (64 * slots) / p->nVDtiles));
+  maxPC = std::min<uint64_t>(maxPC, 4096);
+  double best = -1.0; uint32_t bestN = 1;
+  for (uint64_t n = 1; n <= maxPC; n++) {
+    const uint64_t blocks = (uint64_t)p->nVDtiles * n;
+    const uint64_t waves = (blocks + slots - 1) / slots;
+    const double eff = (double)blocks / (double)(waves * slots);
+    if (eff >= best - 1e-12) { best = eff; bestN = (uint32_t)n; }
+  }
+  p->nPC = bestN;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srb_version(void) { return SRB_ABI_VERSION; }
+const char* srb_last_error(void) { return g_err.c_str(); }
+
+int srb_num_spectra(int mode, int comp) {
+  if (mode != SRB_MODE_FAR && mode != SRB_MODE_NEAR) return -1;
+  switch (comp) {
+    case SRB_COMP_TOTAL: return 1;
+    case SRB_COMP_CARTESIAN: return 3;
+    case SRB_COMP_CARTESIAN_COMPLEX: return 6;
+    case SRB_COMP_SPHERIC: return mode == SRB_MODE_FAR ? 3 : -1;
+    case SRB_COMP_SPHERIC_COMPLEX: return mode == SRB_MODE_FAR ? 6 : -1;
+    default: return -1;
+  }
+}
+
+size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks) {
+  if (validate(grid, tracks) != 0) return 0;
+  Plan p;
+  if (make_plan(grid, tracks, 0, true, &p) != 0) return 0;
+  return (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double);
+}
+
+int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int n_spectra,
+                  void* scratch, size_t scratch_bytes, uint64_t* counters, void* stream_) {
+  if (validate(g, t) != 0) return -1;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Plan p;
+  if (make_plan(g, t, scratch ? scratch_bytes : 0, false, &p) != 0) return -1;
+  if (n_spectra != p.nOut || !spectra) return fail("n_spectra does not match comp");
+  for (int c = 0; c < p.nOut; c++) if (!spectra[c]) return fail("null spectrum buffer");
+  std::memset(&g_info, 0, sizeof g_info);
+  if (counters) SRB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(uint64_t), stream));
+  if (t->nTracks == 0) return 0;
+
+  srb::Params P;
+  std::memset(&P, 0, sizeof P);
+  P.mode = g->mode; P.comp = g->comp;
+  P.nOmega = g->nOmega; P.nA2 = g->nAxis2; P.nPhi = g->nPhi; P.nSnaps = g->nSnaps;
+  P.omega = g->omega;
+  P.axA = g->mode == SRB_MODE_FAR ? g->sinTheta : g->radius;
+  P.axB = g->mode == SRB_MODE_FAR ? g->cosTheta : nullptr;
+  P.sinPhi = g->sinPhi; P.cosPhi = g->cosPhi; P.formFactor = g->formFactor;
+  P.L = g->L_screen; P.dt = g->dt;
+  P.descending = g->omega_last_host < g->omega_first_host ? 1 : 0;
+  P.domega = g->nOmega > 1 ? (g->omega_last_host - g->omega_first_host) / (double)(g->nOmega - 1) : 0.0;
+  P.chunkNodes = p.chunkNodes; P.nChunks = p.nChunks; P.nVD = p.nVD;
+  P.nTracks = t->nTracks;
+  P.x = t->x; P.y = t->y; P.z = t->z; P.ux = t->ux; P.uy = t->uy; P.uz = t->uz;
+  P.offsets = t->offsets; P.w = t->w; P.itStart = t->itStart; P.itEnd = t->itEnd; P.itSnaps = t->itSnaps;
+  P.snapStride = t->itSnapsStride;
+  for (int c = 0; c < p.nOut; c++) P.out[c] = spectra[c];
+  P.slabs = (double*)scratch; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
+  P.counters = (unsigned long long*)counters;
+
+  uint32_t launched = 0;
+  if (p.nPC > 1) SRB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double), stream));
+  const uint32_t blocks = p.nVDtiles * p.nPC;
+  p.L.kernel<<<blocks, NW * 32, p.L.smem, stream>>>(P);
+  SRB_CUDA(cudaGetLastError());
+  launched++;
+  if (p.nPC > 1) {
+    const size_t n = p.slabDoubles;
+    const int rb = (int)std::min<size_t>((n + 255) / 256, (size_t)p.numSM * 8);
+    k_reduce_slabs<<<rb, 256, 0, stream>>>(P, p.nOut, p.perOut);
+    SRB_CUDA(cudaGetLastError());
+    launched++;
+  }
+  g_info.kind = p.kind; g_info.tile_width = p.tw; g_info.chunk_nodes = p.chunkNodes; g_info.n_chunks = p.nChunks;
+  g_info.n_virtual_dirs = p.nVD; g_info.n_particle_chunks = p.nPC; g_info.grid_blocks = blocks;
+  g_info.block_threads = NW * 32; g_info.smem_bytes = (uint32_t)p.L.smem; g_info.kernels_launched = launched;
+  return 0;
+}
+
+int srb_last_launch(srb_launch_info* info) {
+  if (!info) return fail("null info");
+  *info = g_info;
+  return 0;
+}
+
+int srb_swap_axes(const double* src, double* dst, uint32_t nSnaps, uint32_t nO, uint32_t nA, uint32_t nP, void* stream) {
+  if (!src || !dst) return fail("null buffer");
+  const size_t n = (size_t)nSnaps * nO * nA * nP;
+  if (n == 0) return 0;
+  int dev = 0, numSM = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)numSM * 8);
+  k_swap_axes<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, nSnaps, nO, nA, nP);
+  SRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srb_integrate_host(const srb_grid* g, const srb_tracks* t, double* const* spectra, int n_spectra,
+                       uint64_t* counters_host, int device) {
+  if (validate(g, t) != 0) return -1;
+  SRB_CUDA(cudaSetDevice(device));
+  const int nOut = srb_num_spectra(g->mode, g->comp);
+  if (n_spectra != nOut || !spectra) return fail("n_spectra does not match comp");
+  const size_t es = g->dtype == SRB_DTYPE_F64 ? 8 : 4;
+  std::vector<void*> owned;
+  auto cleanup = [&]() { for (void* q : owned) cudaFree(q); };
+  cudaError_t err = cudaSuccess;
+  auto up = [&](const void* h, size_t bytes) -> void* {
+    if (!h || bytes == 0 || err != cudaSuccess) return nullptr;
+    void* d = nullptr;
+    err = cudaMalloc(&d, bytes);
+    if (err != cudaSuccess) return nullptr;
+    owned.push_back(d);
+    err = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice);
+    return d;
+  };
+  srb_grid gd = *g; srb_tracks td = *t;
+  gd.omega = up(g->omega, g->nOmega * es);
+  gd.sinTheta = up(g->sinTheta, g->nAxis2 * es); gd.cosTheta = up(g->cosTheta, g->nAxis2 * es);
+  gd.radius = up(g->radius, g->nAxis2 * es);
+  gd.sinPhi = up(g->sinPhi, g->nPhi * es); gd.cosPhi = up(g->cosPhi, g->nPhi * es);
+  gd.formFactor = up(g->formFactor, g->nOmega * es);
+  const uint64_t total = t->totalSteps_host;
+  td.x = up(t->x, total * es); td.y = up(t->y, total * es); td.z = up(t->z, total * es);
+  td.ux = up(t->ux, total * es); td.uy = up(t->uy, total * es); td.uz = up(t->uz, total * es);
+  td.offsets = (const uint64_t*)up(t->offsets, (size_t)(t->nTracks + 1) * 8);
+  td.w = up(t->w, t->nTracks * es);
+  td.itStart = (const uint32_t*)up(t->itStart, (size_t)t->nTracks * 4);
+  td.itEnd = (const uint32_t*)up(t->itEnd, (size_t)t->nTracks * 4);
+  td.itSnaps = (const uint32_t*)up(t->itSnaps, (size_t)(t->itSnapsStride ? (size_t)t->nTracks * g->nSnaps : g->nSnaps) * 4);
+  if (err != cudaSuccess) { cleanup(); return fail(std::string("upload: ") + cudaGetErrorString(err)); }
+  const size_t per = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
+  std::vector<double*> dsp(nOut);
+  for (int c = 0; c < nOut; c++) {
+    void* d = nullptr; err = cudaMalloc(&d, per * 8);
+    if (err == cudaSuccess) { owned.push_back(d); err = cudaMemset(d, 0, per * 8); }
+    if (err != cudaSuccess) { cleanup(); return fail(std::string("spectrum alloc: ") + cudaGetErrorString(err)); }
+    dsp[c] = (double*)d;
+  }
+  size_t sb = t->nTracks ? srb_scratch_bytes(&gd, &td) : 0;
+  void* scratch = nullptr;
+  if (sb) { if (cudaMalloc(&scratch, sb) == cudaSuccess) owned.push_back(scratch); else { scratch = nullptr; sb = 0; cudaGetLastError(); } }
+  uint64_t* dcnt = nullptr;
+  if (counters_host) { if (cudaMalloc((void**)&dcnt, 16) == cudaSuccess) owned.push_back(dcnt); else dcnt = nullptr; }
+  int rc = srb_integrate(&gd, &td, dsp.data(), nOut, scratch, sb, dcnt, nullptr);
+  if (rc == 0) {
+    std::vector<double> h(per);
+    for (int c = 0; c < nOut && err == cudaSuccess; c++) {
+      err = cudaMemcpy(h.data(), dsp[c], per * 8, cudaMemcpyDeviceToHost);
+      if (err == cudaSuccess) for (size_t i = 0; i < per; i++) spectra[c][i] += h[i];
+    }
+    if (err == cudaSuccess && dcnt) err = cudaMemcpy(counters_host, dcnt, 16, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) rc = fail(std::string("download: ") + cudaGetErrorString(err));
+  }
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

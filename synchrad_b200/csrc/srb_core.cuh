@@ -1,0 +1,625 @@
+// synchrad_b200 — warp-level core of the spectral-integration kernels (sm_100a).
+//
+// Replaces the per-node OpenCL loops of the reference (kernel_farfield.cl:30-108 and the four
+// epilogue variants; kernel_nearfield.cl:29-103 and two variants) with a batched, warp-autonomous
+// formulation.  This is NOT a translation of those kernels:
+//
+//   reference: one work-item per (omega,theta,phi) node, serial over steps, one launch per
+//              particle, every node recomputes beta/gamma/acceleration and calls sin+cos.
+//   here:      one WARP owns a "virtual direction" (theta|R, phi, omega-chunk) for a whole slice of
+//              particles.  Steps are processed in sub-batches of 32:
+//                 prep phase  (lane = time step): everything that does not depend on omega —
+//                     tau = t - n.r, the Lienard-Wiechert vector A, the Nyquist cut-off range and,
+//                     for uniform omega grids, phasor seeds for 16 omega-tiles — is computed ONCE per
+//                     (direction, step), in the reference's exact operation order and without FMA
+//                     contraction (SURVEY §7 "hard parts"), and staged in shared memory;
+//                 main phase  (lane = omega tile): each thread sweeps its tile with a three-term
+//                     phasor recurrence v[k+1] = 2cos(d)*v[k] - v[k-1] (cos and sin parts live in
+//                     different lanes) and accumulates A*v into registers: 8 FP64 issue slots per
+//                     (particle,step,node) update instead of ~30 with a per-node sincos.
+//              Non-uniform grids ('wavelengthGrid', 'logGrid', calc.py:390-399) use the DIRECT
+//              main phase (per-node sincos of the same rounded phase the reference forms).
+//              |A|^2*w is added to the spectrum once per (track, snapshot) by the owning thread —
+//              no per-step global traffic, no atomics (deterministic).
+//
+// The file is written so that the same code can be compiled by g++ for a single-warp CPU
+// emulation (tests/emu/, test infrastructure only: it lets the kernel logic be debugged in a
+// container without a GPU).  The product never runs it on the CPU.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define SRB_HD __host__ __device__ __forceinline__
+#else
+#define SRB_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define SRB_LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u);
+#define SRB_LANES_END } __syncwarp();
+#define SRB_ST (st[0])
+#else
+#define SRB_LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define SRB_LANES_END }
+#define SRB_ST (st[lane])
+#endif
+
+namespace srb {
+
+enum { MODE_FAR = 0, MODE_NEAR = 1 };
+enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
+enum { KIND_DIRECT = 0, KIND_RECUR = 1 };
+constexpr int SUB = 32;  // steps per sub-batch (= lanes of the prep phase)
+
+// ---- strict (uncontracted, round-to-nearest) double arithmetic: the oracle's operation order
+SRB_HD double smul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+SRB_HD double sadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+SRB_HD double ssub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+SRB_HD double sdiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+SRB_HD double ssqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  return __dsqrt_rn(a);
+#else
+  return sqrt(a);
+#endif
+}
+SRB_HD double sdot3(double ax, double ay, double az, double bx, double by, double bz) {
+  return sadd(sadd(smul(ax, bx), smul(ay, by)), smul(az, bz));  // OpenCL dot(), Q8 association
+}
+SRB_HD void sincos_d(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+SRB_HD void sincos_t(double x, double* s, double* c) { sincos_d(x, s, c); }
+SRB_HD double tmul(double a, double b) { return smul(a, b); }
+SRB_HD float tmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+SRB_HD void sincos_t(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+// fp32 'native' path (calc.py:612-615 -> native_sin/native_cos): explicit 2-term Cody-Waite
+// reduction to [-pi,pi] in fp32, then the MUFU approximations.
+SRB_HD void sincos_native(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  const float q = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-q, 6.2831854820251465f, x);     // 2*pi rounded to fp32
+  r = fmaf(-q, -1.7484555e-7f, r);                // 2*pi - fp32(2*pi)
+  __sincosf(r, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+
+// ---- kernel parameter block (plain data, passed by value)
+struct Params {
+  // grid (calc.py:486-512 tables, in the compute dtype TI)
+  int32_t mode, comp;
+  uint32_t nOmega, nA2, nPhi, nSnaps;
+  const void *omega, *axA, *axB, *sinPhi, *cosPhi, *formFactor;
+  double L, dt;
+  int32_t descending;   // omega table is descending ('wavelengthGrid')
+  double domega;        // uniform spacing of the 2*pi*omega table (recurrence kernels only)
+  uint32_t chunkNodes;  // omega nodes per virtual direction
+  uint32_t nChunks;
+  uint32_t nVD;         // nPhi * nA2 * nChunks
+  // tracks (SoA, concatenated)
+  uint32_t nTracks;
+  const void *x, *y, *z, *ux, *uy, *uz;
+  const uint64_t* offsets;  // [nTracks+1]
+  const void* w;            // [nTracks] TI
+  const uint32_t *itStart, *itEnd, *itSnaps;
+  uint32_t snapStride;      // 0: one itSnaps[nSnaps] for all tracks, else per-track stride
+  // output: fp64 spectra in the reference's device layout (nSnaps, nPhi, nA2, nOmega)
+  double* out[6];
+  double* slabs;            // (nPC-1) private partial spectra, reduced afterwards
+  size_t slabStride;        // doubles per slab = nOut*nSnaps*nTotal
+  uint32_t nPC;             // particle chunks
+  unsigned long long* counters;  // [0] passed updates, [1] all updates (may be null)
+};
+
+template <class TI_, class TM_, int MODE_, int KIND_, int TW_, bool NATIVE_>
+struct Cfg {
+  using TI = TI_;   // dtype of tables / tracks
+  using TM = TM_;   // arithmetic type of the main phase
+  static constexpr int MODE = MODE_, KIND = KIND_, TW = TW_;
+  static constexpr bool NATIVE = NATIVE_;
+  static constexpr int TILES = (KIND_ == KIND_RECUR) ? 16 : 32;   // omega tiles per chunk
+  static constexpr int CHUNK = TILES * TW_;
+  static constexpr int NACC = (KIND_ == KIND_RECUR && MODE_ == MODE_FAR) ? 3 * TW_ : 6 * TW_;
+  static constexpr int NREC = (MODE_ == MODE_FAR) ? 4 : 8;
+  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 64 : 1;
+};
+
+template <class C>
+struct WarpSmem {
+  typename C::TM rec[SUB][C::NREC];       // far: A[3], coef|tau ; near: B[3], C[3], coef|tau
+  uint32_t rng[SUB];                      // lo | hi<<10 | flag<<30 (chunk-relative pass range)
+  typename C::TM seeds[C::NSEED][SUB + 1];  // [(sel*2+part)*16+tile][step], padded
+};
+
+template <class C>
+struct ThreadState {
+  typename C::TM acc[C::NACC];
+  typename C::TM wl[C::KIND == KIND_DIRECT ? C::TW : 1];   // direct kind: this lane's omega nodes
+  unsigned long long nPass, nAll;
+};
+
+struct Geom {            // one virtual direction
+  uint32_t iPhi, iA2, cLo, cHi;   // omega nodes [cLo, cHi)
+  double nx, ny, nz;     // far: unit vector n ; near: point on the screen
+  double tx, ty, tz, px, py, pz;  // far spheric: e_theta, e_phi
+};
+
+struct TrackView {
+  const void *x, *y, *z, *ux, *uy, *uz;   // already offset to the track start
+  uint32_t n, itStart, itEnd;
+  const uint32_t* snaps;
+  double w;
+};
+
+template <class TI> SRB_HD double ldv(const void* p, size_t i) { return (double)((const TI*)p)[i]; }
+
+// -------------------------------------------------------------------------------- prep phase
+// Everything below is per (direction, step) and follows the oracle's operation order exactly
+// (no contraction), so that for TI=double tau and the amplitude vector are bit-identical to the
+// strict restatement of kernel_farfield.cl:65-94 / kernel_nearfield.cl:64-85.
+template <class C>
+SRB_HD void prep_far(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
+                     double dtInv, double& tau, double& tauPrev, double A[3]) {
+  using TI = typename C::TI;
+  const double time = smul((double)(tv.itStart + it), P.dt);
+  tau = ssub(time, sdot3(ldv<TI>(tv.x, it), ldv<TI>(tv.y, it), ldv<TI>(tv.z, it), g.nx, g.ny, g.nz));
+  if (it == 0) tauPrev = 0.0;   // phasePrev starts at 0 (Q1)
+  else {
+    const double tp = smul((double)(tv.itStart + it - 1), P.dt);
+    tauPrev = ssub(tp, sdot3(ldv<TI>(tv.x, it - 1), ldv<TI>(tv.y, it - 1), ldv<TI>(tv.z, it - 1),
+                             g.nx, g.ny, g.nz));
+  }
+  double u0 = ldv<TI>(tv.ux, it), u1 = ldv<TI>(tv.uy, it), u2 = ldv<TI>(tv.uz, it);
+  double v0 = ldv<TI>(tv.ux, it + 1), v1 = ldv<TI>(tv.uy, it + 1), v2 = ldv<TI>(tv.uz, it + 1);
+  double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
+  u0 = smul(u0, gi); u1 = smul(u1, gi); u2 = smul(u2, gi);
+  gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(v0, v1, v2, v0, v1, v2))));
+  v0 = smul(v0, gi); v1 = smul(v1, gi); v2 = smul(v2, gi);
+  const double a0 = smul(ssub(v0, u0), dtInv), a1 = smul(ssub(v1, u1), dtInv), a2 = smul(ssub(v2, u2), dtInv);
+  const double b0 = smul(0.5, sadd(v0, u0)), b1 = smul(0.5, sadd(v1, u1)), b2 = smul(0.5, sadd(v2, u2));
+  double c1 = sdot3(a0, a1, a2, g.nx, g.ny, g.nz);
+  double c2 = ssub(1.0, sdot3(b0, b1, b2, g.nx, g.ny, g.nz));
+  c2 = sdiv(1.0, c2);
+  c1 = smul(smul(c1, c2), c2);
+  const double A0 = ssub(smul(c1, ssub(g.nx, b0)), smul(c2, a0));
+  const double A1 = ssub(smul(c1, ssub(g.ny, b1)), smul(c2, a1));
+  const double A2 = ssub(smul(c1, ssub(g.nz, b2)), smul(c2, a2));
+  if (P.comp == COMP_SPH || P.comp == COMP_SPH_CPLX) {   // kernel_farfield.cl:442-445
+    A[0] = sdot3(g.nx, g.ny, g.nz, A0, A1, A2);
+    A[1] = sdot3(g.tx, g.ty, g.tz, A0, A1, A2);
+    A[2] = sdot3(g.px, g.py, g.pz, A0, A1, A2);
+  } else { A[0] = A0; A[1] = A1; A[2] = A2; }
+}
+
+template <class C>
+SRB_HD void near_tau(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
+                     double& tau, double& r0, double& r1, double& r2, double& rL) {
+  using TI = typename C::TI;
+  const double time = smul((double)(tv.itStart + it), P.dt);
+  r0 = ssub(g.nx, ldv<TI>(tv.x, it)); r1 = ssub(g.ny, ldv<TI>(tv.y, it)); r2 = ssub(g.nz, ldv<TI>(tv.z, it));
+  rL = ssqrt(sdot3(r0, r1, r2, r0, r1, r2));
+  tau = sadd(time, rL);
+}
+
+// near: B = rInv*(beta - n), Cv = rInv^2 * n ; the reference's c1 = omega*B, c2 = Cv
+template <class C>
+SRB_HD void prep_near(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
+                      double& tau, double& tauPrev, double B[3], double Cv[3]) {
+  using TI = typename C::TI;
+  double r0, r1, r2, rL;
+  near_tau<C>(P, g, tv, it, tau, r0, r1, r2, rL);
+  if (it == 0) tauPrev = 0.0;
+  else { double q0, q1, q2, qL; near_tau<C>(P, g, tv, it - 1, tauPrev, q0, q1, q2, qL); }
+  const double rInv = sdiv(1.0, rL);
+  const double n0 = smul(rInv, r0), n1 = smul(rInv, r1), n2 = smul(rInv, r2);
+  double u0 = ldv<TI>(tv.ux, it), u1 = ldv<TI>(tv.uy, it), u2 = ldv<TI>(tv.uz, it);
+  const double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
+  u0 = smul(u0, gi); u1 = smul(u1, gi); u2 = smul(u2, gi);
+  B[0] = smul(rInv, ssub(u0, n0)); B[1] = smul(rInv, ssub(u1, n1)); B[2] = smul(rInv, ssub(u2, n2));
+  const double ri2 = smul(rInv, rInv);
+  Cv[0] = smul(ri2, n0); Cv[1] = smul(ri2, n1); Cv[2] = smul(ri2, n2);
+}
+
+// Nyquist guard (kernel_farfield.cl:68-72), hoisted: for fixed (direction, step) the test
+// |fl(w_j*tau) - fl(w_j*tauPrev)| < pi is monotone in omega, so the passing nodes of a chunk form
+// one interval.  Its end is found by bisection on the reference's EXACT rounded predicate, so the
+// per-node decisions are reproduced.  Returns chunk-relative [lo, hi).
+template <class C>
+SRB_HD void pass_range(const Params& P, const Geom& g, double tau, double tauPrev,
+                       uint32_t& lo, uint32_t& hi) {
+  using TI = typename C::TI;
+  const TI* om = (const TI*)P.omega;
+  auto pass = [&](uint32_t j) -> bool {
+    const double w = (double)om[j];
+    return fabs(ssub(smul(w, tau), smul(w, tauPrev))) < 3.14159265358979323846;
+  };
+  const uint32_t n = g.cHi - g.cLo;
+  const uint32_t jSmall = P.descending ? g.cHi - 1 : g.cLo;   // smallest omega of the chunk
+  const uint32_t jLarge = P.descending ? g.cLo : g.cHi - 1;
+  if (pass(jLarge)) { lo = 0; hi = n; return; }
+  if (!pass(jSmall)) { lo = 0; hi = 0; return; }
+  // invariant: pass(a) true, pass(b) false, a and b chunk-relative positions ordered by omega
+  uint32_t a = 0, b = n - 1;            // positions in ascending-omega order
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) >> 1;
+    const uint32_t j = P.descending ? g.cHi - 1 - mid : g.cLo + mid;
+    if (pass(j)) a = mid; else b = mid;
+  }
+  if (P.descending) { lo = n - b; hi = n; } else { lo = 0; hi = b; }
+}
+
+// Phasor seeds for the 16 omega tiles of a chunk (uniform grid): X_m = exp(i(phi0 + m*TW*d)),
+// Y_m = X_m * exp(i*d), generated with the three-term recurrence in m.  phi0 is the reference's
+// own rounded phase at the chunk's first node.
+template <class C>
+SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& sm, int s, double& coef) {
+  using TI = typename C::TI; using TM = typename C::TM;
+  const double w0 = (double)((const TI*)P.omega)[g.cLo];
+  double s0, c0, sd, cd;
+  sincos_d(smul(w0, tau), &s0, &c0);
+  sincos_d(P.domega * tau, &sd, &cd);
+  coef = 2.0 * cd;
+  double cw = cd, sw = sd;
+#pragma unroll
+  for (int i = 1; i < C::TW; i <<= 1) { const double t = cw * cw - sw * sw; sw = 2.0 * cw * sw; cw = t; }
+  double xr0 = c0, xi0 = s0;
+  double xr1 = c0 * cw - s0 * sw, xi1 = c0 * sw + s0 * cw;
+  double yr0 = c0 * cd - s0 * sd, yi0 = c0 * sd + s0 * cd;
+  double yr1 = xr1 * cd - xi1 * sd, yi1 = xr1 * sd + xi1 * cd;
+  const double cf = 2.0 * cw;
+  sm.seeds[0][s] = (TM)xr0;  sm.seeds[16][s] = (TM)xi0;  sm.seeds[32][s] = (TM)yr0;  sm.seeds[48][s] = (TM)yi0;
+  sm.seeds[1][s] = (TM)xr1;  sm.seeds[17][s] = (TM)xi1;  sm.seeds[33][s] = (TM)yr1;  sm.seeds[49][s] = (TM)yi1;
+#pragma unroll
+  for (int m = 2; m < 16; m++) {
+    const double xr2 = cf * xr1 - xr0, xi2 = cf * xi1 - xi0, yr2 = cf * yr1 - yr0, yi2 = cf * yi1 - yi0;
+    sm.seeds[m][s] = (TM)xr2; sm.seeds[16 + m][s] = (TM)xi2; sm.seeds[32 + m][s] = (TM)yr2; sm.seeds[48 + m][s] = (TM)yi2;
+    xr0 = xr1; xi0 = xi1; yr0 = yr1; yi0 = yi1; xr1 = xr2; xi1 = xi2; yr1 = yr2; yi1 = yi2;
+  }
+}
+
+template <class C>
+SRB_HD void prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint32_t itBase, int cnt,
+                       double dtInv, int lane, WarpSmem<C>& sm, ThreadState<C>& st) {
+  using TM = typename C::TM;
+  if (lane >= cnt) return;
+  const uint32_t it = itBase + (uint32_t)lane;
+  double tau, tauPrev, V[6];
+  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, tau, tauPrev, V);
+  else prep_near<C>(P, g, tv, it, tau, tauPrev, V, V + 3);
+  uint32_t lo, hi;
+  pass_range<C>(P, g, tau, tauPrev, lo, hi);
+  const uint32_t n = g.cHi - g.cLo;
+  const uint32_t flag = (hi <= lo) ? 0u : ((lo == 0 && hi == n) ? 1u : 2u);
+  sm.rng[lane] = lo | (hi << 10) | (flag << 30);
+  st.nPass += hi - lo; st.nAll += n;
+  double last = tau;
+  if (C::KIND == KIND_RECUR && flag) make_seeds<C>(P, g, tau, sm, lane, last);
+  constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
+#pragma unroll
+  for (int k = 0; k < NV; k++) sm.rec[lane][k] = (TM)V[k];
+  sm.rec[lane][NV] = (TM)last;   // recurrence: 2cos(d) ; direct: tau
+}
+
+// -------------------------------------------------------------------------------- main phase
+template <class C>
+SRB_HD void main_recur(const WarpSmem<C>& sm, int cnt, int lane, ThreadState<C>& st) {
+  using TM = typename C::TM;
+  constexpr int TW = C::TW;
+  constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
+  const int m = lane & 15;
+  for (int s = 0; s < cnt; s++) {
+    const uint32_t r = sm.rng[s];
+    const uint32_t flag = r >> 30;
+    if (flag == 0) continue;          // warp-uniform: nothing passes the guard at this step
+    TM V[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
+    const TM coef = sm.rec[s][NV];
+    TM vm = sm.seeds[lane][s], v = sm.seeds[32 + lane][s];
+    if (flag == 1) {
+#pragma unroll
+      for (int c = 0; c < NV; c++) st.acc[c] = fma(V[c], vm, st.acc[c]);
+#pragma unroll
+      for (int c = 0; c < NV; c++) st.acc[NV + c] = fma(V[c], v, st.acc[NV + c]);
+#pragma unroll
+      for (int k = 2; k < TW; k++) {
+        const TM vn = fma(coef, v, -vm); vm = v; v = vn;
+#pragma unroll
+        for (int c = 0; c < NV; c++) st.acc[k * NV + c] = fma(V[c], v, st.acc[k * NV + c]);
+      }
+    } else {
+      const int lo = (int)(r & 0x3ffu) - m * TW, hi = (int)((r >> 10) & 0x3ffu) - m * TW;
+      if (hi <= 0 || lo >= TW) continue;
+#pragma unroll
+      for (int k = 0; k < TW; k++) {
+        TM cur;
+        if (k == 0) cur = vm; else if (k == 1) cur = v;
+        else { const TM vn = fma(coef, v, -vm); vm = v; v = vn; cur = vn; }
+        if (k >= lo && k < hi) {
+#pragma unroll
+          for (int c = 0; c < NV; c++) st.acc[k * NV + c] = fma(V[c], cur, st.acc[k * NV + c]);
+        }
+      }
+    }
+  }
+}
+
+// Direct main phase: lane = tile of TW nodes, per-node sincos of the reference's rounded phase.
+template <class C>
+SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, int lane,
+                        ThreadState<C>& st) {
+  using TM = typename C::TM;
+  constexpr int TW = C::TW;
+  constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
+  for (int s = 0; s < cnt; s++) {
+    const uint32_t r = sm.rng[s];
+    if ((r >> 30) == 0) continue;
+    const int lo = (int)(r & 0x3ffu) - lane * TW, hi = (int)((r >> 10) & 0x3ffu) - lane * TW;
+    if (hi <= 0 || lo >= TW) continue;
+    TM V[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
+    const TM tau = sm.rec[s][NV];
+#pragma unroll
+    for (int k = 0; k < TW; k++) {
+      if (k >= lo && k < hi) {
+        TM sn, cs;
+        const TM ph = tmul(st.wl[k], tau);  // single rounding == the reference's omega*(time - n.r)
+        if (C::NATIVE) sincos_native((float)ph, (float*)&sn, (float*)&cs); else sincos_t(ph, &sn, &cs);
+        if (C::MODE == MODE_FAR) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            st.acc[k * 6 + c] = fma(V[c], cs, st.acc[k * 6 + c]);
+            st.acc[k * 6 + 3 + c] = fma(V[c], sn, st.acc[k * 6 + 3 + c]);
+          }
+        } else {
+          const TM t1 = st.wl[k] * sn, t2 = st.wl[k] * cs;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {   // Re += -c1*sin + c2*cos ; Im += c1*cos + c2*sin
+            st.acc[k * 6 + c] = fma(V[3 + c], cs, fma(-V[c], t1, st.acc[k * 6 + c]));
+            st.acc[k * 6 + 3 + c] = fma(V[3 + c], sn, fma(V[c], t2, st.acc[k * 6 + 3 + c]));
+          }
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- flush
+// Adds this track's contribution to snapshot iSnap (kernel_farfield.cl:100-106 and variants).
+// Accumulators are NOT reset (cumulative snapshots, Q3).  `xchg(state, idx)` returns the
+// value `f(partner lane)`; on the GPU it is a shuffle, in the emulator a direct read.
+template <class C>
+SRB_HD double* dest(const Params& P, uint32_t pc, int c) {
+  const size_t nTotal = (size_t)P.nOmega * P.nA2 * P.nPhi;
+  return pc == 0 ? P.out[c] : P.slabs + (size_t)(pc - 1) * P.slabStride + (size_t)c * P.nSnaps * nTotal;
+}
+
+// Split layout (recurrence kernels): lanes l and l^16 hold the cos and sin parts of the same 16
+// tiles, so the partner's accumulators of node k are fetched (GPU: shuffles; emulator: direct
+// read) and both lanes reconstruct the full complex amplitude; lane part 0 then writes.
+template <class C>
+SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint32_t pc, uint32_t iSnap,
+                       int lane, const ThreadState<C>* st) {
+  using TI = typename C::TI; using TM = typename C::TM;
+  constexpr int TW = C::TW;
+  constexpr int NV = C::NACC / TW;
+#if defined(__CUDA_ARCH__)
+  const ThreadState<C>& me = st[0];
+#else
+  const ThreadState<C>& me = st[lane];
+#endif
+  const size_t nTotal = (size_t)P.nOmega * P.nA2 * P.nPhi;
+  const bool cplx = (P.comp == COMP_CART_CPLX || P.comp == COMP_SPH_CPLX);
+  const double wpdt2 = smul(smul(tv.w, P.dt), P.dt);
+  const double wpdt = smul(ssqrt(tv.w), P.dt);
+  const bool useFF = (C::MODE == MODE_FAR && P.comp == COMP_CART_CPLX && P.formFactor != nullptr);
+  const int tile = (C::KIND == KIND_RECUR) ? (lane & 15) : lane;
+  const int part = (C::KIND == KIND_RECUR) ? (lane >> 4) : 0;
+#pragma unroll
+  for (int k = 0; k < TW; k++) {
+    const uint32_t j = g.cLo + (uint32_t)(tile * TW + k);
+    const bool valid = j < g.cHi;
+    const size_t idx = (size_t)j + (size_t)P.nOmega * (g.iA2 + (size_t)P.nA2 * g.iPhi) + nTotal * iSnap;
+    double re[3], im[3];
+    if (C::KIND == KIND_DIRECT) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { re[c] = (double)me.acc[k * 6 + c]; im[c] = (double)me.acc[k * 6 + 3 + c]; }
+    } else {
+      double ma[NV], pa[NV];
+#pragma unroll
+      for (int c = 0; c < NV; c++) {
+        ma[c] = (double)me.acc[k * NV + c];
+#if defined(__CUDA_ARCH__)
+        pa[c] = __shfl_xor_sync(0xffffffffu, ma[c], 16);
+#else
+        pa[c] = (double)st[lane ^ 16].acc[k * NV + c];
+#endif
+      }
+      const double* cosS = part ? pa : ma;
+      const double* sinS = part ? ma : pa;
+      if (C::MODE == MODE_FAR) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { re[c] = cosS[c]; im[c] = sinS[c]; }
+      } else {
+        // near: acc = {P = sum B*v, Q = sum Cv*v}; Re = Qcos - w*Psin, Im = Qsin + w*Pcos
+        const double wj = valid ? (double)((const TI*)P.omega)[j] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          re[c] = cosS[(NV > 3 ? 3 : 0) + c] - wj * sinS[c];
+          im[c] = sinS[(NV > 3 ? 3 : 0) + c] + wj * cosS[c];
+        }
+      }
+    }
+    if (!valid) continue;
+    if (!cplx) {
+      if (part == 0) {
+        if (P.comp == COMP_TOTAL) {
+          dest<C>(P, pc, 0)[idx] += wpdt2 * (((re[0] * re[0] + re[1] * re[1]) + re[2] * re[2]) +
+                                             ((im[0] * im[0] + im[1] * im[1]) + im[2] * im[2]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; c++) dest<C>(P, pc, c)[idx] += wpdt2 * (re[c] * re[c] + im[c] * im[c]);
+        }
+      }
+    } else {
+      const double ff = useFF ? (double)((const TI*)P.formFactor)[j] : 1.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        if (C::KIND == KIND_DIRECT || part == 0) dest<C>(P, pc, 2 * c)[idx] += wpdt * (re[c] * ff);
+        if (C::KIND == KIND_DIRECT || part == 1) dest<C>(P, pc, 2 * c + 1)[idx] += wpdt * (im[c] * ff);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- warp task
+// One warp integrates all tracks of particle chunk `pc` for virtual direction `vd`.
+template <class C>
+SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm, ThreadState<C>* st) {
+  using TI = typename C::TI; using TM = typename C::TM;
+  Geom g;
+  {
+    const uint32_t ch = vd % P.nChunks; const uint32_t d = vd / P.nChunks;
+    g.iA2 = d % P.nA2; g.iPhi = d / P.nA2;
+    g.cLo = ch * P.chunkNodes; g.cHi = g.cLo + P.chunkNodes < P.nOmega ? g.cLo + P.chunkNodes : P.nOmega;
+    const double sP = ldv<TI>(P.sinPhi, g.iPhi), cP = ldv<TI>(P.cosPhi, g.iPhi);
+    if (C::MODE == MODE_FAR) {
+      const double sT = ldv<TI>(P.axA, g.iA2), cT = ldv<TI>(P.axB, g.iA2);
+      if (sizeof(TI) == 8) { g.nx = smul(sT, cP); g.ny = smul(sT, sP); g.nz = cT; g.tx = smul(cT, cP); g.ty = smul(cT, sP); }
+      else {  // the reference forms n in fp32 (kernel_farfield.cl:40-42)
+        g.nx = (double)((float)sT * (float)cP); g.ny = (double)((float)sT * (float)sP); g.nz = cT;
+        g.tx = (double)((float)cT * (float)cP); g.ty = (double)((float)cT * (float)sP);
+      }
+      g.tz = -sT; g.px = -sP; g.py = cP; g.pz = 0.0;
+    } else {
+      const double r = ldv<TI>(P.axA, g.iA2);
+      if (sizeof(TI) == 8) { g.nx = smul(r, cP); g.ny = smul(r, sP); }
+      else { g.nx = (double)((float)r * (float)cP); g.ny = (double)((float)r * (float)sP); }
+      g.nz = P.L;
+      g.tx = g.ty = g.tz = g.px = g.py = g.pz = 0.0;
+    }
+  }
+  // particle chunk -> track range, balanced by cumulative steps (offsets is a prefix sum)
+  uint32_t t0, t1;
+  {
+    const uint64_t total = P.offsets[P.nTracks];
+    auto bound = [&](uint32_t c) -> uint32_t {
+      if (c == 0) return 0u;
+      if (c >= P.nPC) return P.nTracks;
+      const uint64_t target = (total / P.nPC) * c + ((total % P.nPC) * c) / P.nPC;
+      uint32_t a = 0, b = P.nTracks;      // first track whose start offset >= target
+      while (a < b) { const uint32_t mid = (a + b) >> 1; if (P.offsets[mid] < target) a = mid + 1; else b = mid; }
+      return a;
+    };
+    t0 = bound(pc); t1 = bound(pc + 1);
+  }
+  const double dtInv = sdiv(1.0, P.dt);
+  SRB_LANES_BEGIN
+    SRB_ST.nPass = 0; SRB_ST.nAll = 0;
+    if (C::KIND == KIND_DIRECT) {
+#pragma unroll
+      for (int k = 0; k < C::TW; k++) {
+        const uint32_t j = g.cLo + (uint32_t)(lane * C::TW + k);
+        SRB_ST.wl[k] = j < g.cHi ? (TM)((const TI*)P.omega)[j] : (TM)0;
+      }
+    }
+  SRB_LANES_END
+
+  for (uint32_t t = t0; t < t1; t++) {
+    TrackView tv;
+    const uint64_t o = P.offsets[t];
+    tv.n = (uint32_t)(P.offsets[t + 1] - o);
+    tv.x = (const TI*)P.x + o; tv.y = (const TI*)P.y + o; tv.z = (const TI*)P.z + o;
+    tv.ux = (const TI*)P.ux + o; tv.uy = (const TI*)P.uy + o; tv.uz = (const TI*)P.uz + o;
+    tv.itStart = P.itStart[t]; tv.itEnd = P.itEnd[t];
+    tv.snaps = P.itSnaps + (size_t)P.snapStride * t;
+    tv.w = ldv<TI>(P.w, t);
+    SRB_LANES_BEGIN
+#pragma unroll
+      for (int k = 0; k < C::NACC; k++) SRB_ST.acc[k] = (TM)0;
+    SRB_LANES_END
+    // loop bounds of kernel_farfield.cl:59-63 (uint wrap-around for itEnd==0 / nSteps==0 not reproduced)
+    const uint32_t loopEnd = tv.itEnd > 0 ? tv.itEnd - 1 : 0;
+    const uint32_t nComp = tv.n > 0 ? (tv.n - 1 < loopEnd ? tv.n - 1 : loopEnd) : 0;
+    uint32_t iSnap = 0;
+    while (iSnap < P.nSnaps && !(tv.itStart < tv.snaps[iSnap])) iSnap++;   // :54-57
+    uint32_t cur = 0;    // next loop index `it` to process
+    while (iSnap < P.nSnaps) {
+      // the flush test `it_glob + 2 == itSnaps[iSnap]` (:100) fires at it = itf, if reachable
+      const long long itf = (long long)tv.snaps[iSnap] - 2 - (long long)tv.itStart;
+      if (itf < (long long)cur || itf >= (long long)loopEnd) break;   // never fires again (Q3/Q4)
+      const uint32_t stop = (uint32_t)(itf + 1) < nComp ? (uint32_t)(itf + 1) : nComp;
+      for (uint32_t base = cur; base < stop; base += SUB) {
+        const int cnt = (int)(stop - base < (uint32_t)SUB ? stop - base : (uint32_t)SUB);
+        SRB_LANES_BEGIN
+          prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);
+        SRB_LANES_END
+        SRB_LANES_BEGIN
+          if (C::KIND == KIND_RECUR) main_recur<C>(sm, cnt, lane, SRB_ST);
+          else main_direct<C>(P, g, sm, cnt, lane, SRB_ST);
+        SRB_LANES_END
+      }
+      SRB_LANES_BEGIN
+        flush_lane<C>(P, g, tv, pc, iSnap, lane, st);
+      SRB_LANES_END
+      cur = (uint32_t)(itf + 1);
+      iSnap++;
+    }
+  }
+  if (P.counters) {
+    SRB_LANES_BEGIN
+#if defined(__CUDA_ARCH__)
+      if (SRB_ST.nAll) { atomicAdd(P.counters, SRB_ST.nPass); atomicAdd(P.counters + 1, SRB_ST.nAll); }
+#else
+      P.counters[0] += SRB_ST.nPass; P.counters[1] += SRB_ST.nAll;
+#endif
+    SRB_LANES_END
+  }
+}
+
+}  // namespace srb

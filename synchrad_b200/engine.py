@@ -1,0 +1,164 @@
+"""Device plumbing of the hot path: torch tensors as device buffers, ctypes into the C ABI.
+
+Replaces the PyOpenCL context/queue/array layer and the per-particle launch loop of the
+reference (calc.py:257-267, 292-353, 513-558, 573-603).  PyTorch is used for device memory,
+streams and `torch.distributed` only; all arithmetic happens in libsynchrad_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import host
+
+_TORCH = {np.float64: torch.float64, np.float32: torch.float32, np.uint64: torch.int64,
+          np.uint32: torch.int32, np.double: torch.float64, np.single: torch.float32}
+
+
+def _tt(np_dt):
+    return _TORCH[np.dtype(np_dt).type]
+
+
+def require_cuda(device_index):
+    if not torch.cuda.is_available():
+        raise RuntimeError('synchrad_b200 needs a CUDA device (B200, sm_100a); there is no CPU '
+                           'fallback. Use Args["ctx"]=False for an analysis-only object.')
+    n = torch.cuda.device_count()
+    if not (0 <= device_index < n):
+        raise RuntimeError(f'CUDA device {device_index} requested but only {n} visible')
+    return torch.device('cuda', device_index)
+
+
+class PinnedAlloc:
+    """alloc(shape, dtype) -> NumPy view of a pinned torch tensor (keeps the tensors)."""
+
+    def __init__(self, pin=True):
+        self.pin = pin and torch.cuda.is_available()
+        self.tensors = []
+
+    def __call__(self, shape, np_dt):
+        t = torch.empty(shape, dtype=_tt(np_dt), pin_memory=self.pin)
+        self.tensors.append(t)
+        a = t.numpy()
+        return a.view(np_dt) if a.dtype != np.dtype(np_dt) else a
+
+
+class DeviceGrid:
+    """The kernel-side tables of one SynchRad object (the `self.Data[...]` of calc.py:486-512)."""
+
+    def __init__(self, Args, dtype, device):
+        self.device = device
+        self.dtype = dtype
+        self.host = host.grid_tables(Args, dtype)
+        self.dev = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
+        self.uniform = host.omega_is_uniform(Args)
+
+
+class Result:
+    __slots__ = ('spectra', 'counters', 'info', 'updates', 'elapsed_ms', '_keep')
+
+
+def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='auto',
+              counters=True, device_tracks=None, timing=False):
+    """Run the hot path for the packed tracks of this rank.
+
+    Returns Result with `spectra`: list of float64 device tensors (nSnaps, nPhi, nAxis2, nOmega).
+    `device_tracks` (optional) are tracks already resident on the device: a dict with the
+    PackedTracks field names holding torch tensors (used by bench.py's device-resident leg).
+    """
+    lib = _lib.load()
+    dev = grid.device
+    mode = Args['mode']
+    n_out = lib.srb_num_spectra(_lib.MODE[mode], _lib.COMP[comp])
+    if n_out < 0:
+        # the reference would fail with AttributeError at calc.py:342 (no such near kernel)
+        raise AttributeError(f"no {comp!r} kernel in {mode}-field mode")
+    n_w, n_2, n_p = (int(v) for v in Args['gridNodeNums'])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        if device_tracks is None:
+            d = {}
+            names = ('x', 'y', 'z', 'ux', 'uy', 'uz')
+            for nm, a in zip(names, packed.coords):
+                d[nm] = torch.from_numpy(a.view(a.dtype)).to(dev, non_blocking=True)
+            d['offsets'] = torch.from_numpy(packed.offsets.view(np.int64)).to(dev, non_blocking=True)
+            d['w'] = torch.from_numpy(packed.w).to(dev, non_blocking=True)
+            for nm in ('itStart', 'itEnd', 'itSnaps'):
+                d[nm] = torch.from_numpy(getattr(packed, nm).view(np.int32)).to(dev, non_blocking=True)
+            n_tracks, total, stride = packed.n, packed.total, packed.snapStride
+        else:
+            d = device_tracks
+            n_tracks, total, stride = d['n'], d['total'], d['snapStride']
+        ff = None
+        if comp == 'cartesian_complex' and mode == 'far':
+            ff = torch.from_numpy(host.form_factor(Args, dtype)).to(dev)
+
+        g = _lib.srb_grid()
+        g.mode, g.comp, g.dtype = _lib.MODE[mode], _lib.COMP[comp], _lib.DTYPE[
+            'double' if dtype is np.double else 'float']
+        g.native = 1 if native else 0
+        g.phasor = _lib.PHASOR[phasor]
+        g.omega_uniform = 1 if grid.uniform else 0
+        g.nOmega, g.nAxis2, g.nPhi, g.nSnaps = n_w, n_2, n_p, int(nSnaps)
+        T = grid.dev
+        g.omega = T['omega'].data_ptr()
+        g.sinPhi, g.cosPhi = T['sinPhi'].data_ptr(), T['cosPhi'].data_ptr()
+        if mode == 'far':
+            g.sinTheta, g.cosTheta = T['sinTheta'].data_ptr(), T['cosTheta'].data_ptr()
+        else:
+            g.radius = T['radius'].data_ptr()
+            g.L_screen = float(dtype(Args['L_screen']))
+        g.formFactor = ff.data_ptr() if ff is not None else None
+        g.dt = float(dtype(Args['timeStep']))
+        g.omega_first_host = float(grid.host['omega'][0])
+        g.omega_last_host = float(grid.host['omega'][-1])
+
+        t = _lib.srb_tracks()
+        t.nTracks = n_tracks
+        for nm in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'offsets', 'w', 'itStart', 'itEnd', 'itSnaps'):
+            setattr(t, nm, d[nm].data_ptr())
+        t.itSnapsStride = stride
+        t.totalSteps_host = total
+
+        spectra = [torch.zeros((int(nSnaps), n_p, n_2, n_w), dtype=torch.float64, device=dev)
+                   for _ in range(n_out)]
+        sp = (ctypes.c_void_p * n_out)(*[s.data_ptr() for s in spectra])
+        nbytes = lib.srb_scratch_bytes(ctypes.byref(g), ctypes.byref(t)) if n_tracks else 0
+        scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev) if nbytes else None
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev) if counters else None
+        if timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        _lib.check(lib.srb_integrate(
+            ctypes.byref(g), ctypes.byref(t), sp, n_out,
+            scratch.data_ptr() if scratch is not None else None, nbytes,
+            cnt.data_ptr() if cnt is not None else None, ctypes.c_void_p(stream.cuda_stream)))
+        res = Result()
+        res.elapsed_ms = None
+        if timing:
+            e1.record(stream)
+            e1.synchronize()
+            res.elapsed_ms = e0.elapsed_time(e1)
+        info = _lib.srb_launch_info()
+        lib.srb_last_launch(ctypes.byref(info))
+        res.spectra, res.counters, res.info = spectra, cnt, info
+        res.updates = None
+        # keep inputs alive until the stream has consumed them
+        res._keep = (d, ff, scratch)
+        return res
+
+
+def to_host_layout(spectra, nSnaps, n_w, n_2, n_p):
+    """Device-side `swapaxes(-1,-3)` (calc.py:573-577): (nSnaps,nPhi,nA2,nOmega) ->
+    contiguous (nSnaps,nOmega,nA2,nPhi), still on the device."""
+    lib = _lib.load()
+    out = []
+    for s in spectra:
+        dst = torch.empty((int(nSnaps), n_w, n_2, n_p), dtype=torch.float64, device=s.device)
+        with torch.cuda.device(s.device):
+            stream = torch.cuda.current_stream(s.device)
+            _lib.check(lib.srb_swap_axes(s.data_ptr(), dst.data_ptr(), int(nSnaps), n_w, n_2, n_p,
+                                         ctypes.c_void_p(stream.cuda_stream)))
+        out.append(dst)
+    return out

@@ -1,0 +1,198 @@
+"""Host-side (NumPy) logic of the spectral-integration path: the reference's `calc_input`
+grid/dtype semantics and the packing of particle tracks into the batched SoA layout the C ABI
+takes.  Mirrors, behaviourally, these parts of /root/reference/synchrad/calc.py:
+
+    init_args ............. `_init_args`            calc.py:355-451
+    grid_tables ........... `_init_data`            calc.py:486-512
+    form_factor ........... `_init_raditaion`       calc.py:473-480
+    snap_iterations ....... `_set_snap_iterations`  calc.py:626-630
+    select_tracks ......... particle split          calc.py:204-212, 230-236
+    pack_tracks ........... `_track_to_device` + the per-track scalars of `_process_track`
+                            calc.py:579-603, 292-307 — for ALL tracks at once
+"""
+import numpy as np
+
+COMP_KEYS = {
+    'total': ['total'],
+    'cartesian': ['x', 'y', 'z'],
+    'cartesian_complex': ['xre', 'xim', 'yre', 'yim', 'zre', 'zim'],
+    'spheric': ['r', 'theta', 'phi'],
+    'spheric_complex': ['rre', 'rim', 'thetare', 'thetaim', 'phire', 'phiim'],
+}
+
+
+def np_dtype(name):
+    # the reference accepts 'double' and 'float' (calc.py:364-367); its docstring says "single"
+    if name == 'double':
+        return np.double
+    if name in ('float', 'single'):
+        return np.single
+    raise ValueError(f"dtype must be 'double' or 'float', got {name!r}")
+
+
+def init_args(Args):
+    """Fill defaults and build the spectral axes in place (returns (Args, numpy dtype))."""
+    if 'grid' not in Args:
+        raise KeyError("calc_input needs a 'grid' entry")
+    Args.setdefault('mode', 'far')
+    Args.setdefault('dtype', 'double')
+    if Args['mode'] not in ('far', 'near'):
+        raise ValueError(f"mode must be 'far' or 'near', got {Args['mode']!r}")
+    dtype = np_dtype(Args['dtype'])
+    if dtype is np.single:
+        if Args['mode'] == 'far':
+            print('WARNING: Chosen single precision should be used with care '
+                  'for the farfield calculations\n')
+        else:
+            print('WARNING: Chosen single precision is not recommended '
+                  'for the nearfield calculations\n')
+    Args.setdefault('ctx', None)
+    Args.setdefault('Features', [])
+
+    nodes = Args['grid'][-1]
+    Args['gridNodeNums'] = nodes
+    Args['numGridNodes'] = int(np.prod(nodes))
+    n_w, n_2, n_p = (int(v) for v in nodes)
+
+    w_lo, w_hi = Args['grid'][0]
+    omega = np.linspace(w_lo, w_hi, n_w)
+    for feature in Args['Features']:          # first matching feature wins
+        if feature == 'wavelengthGrid':
+            Args['wavelengths'] = np.linspace(1. / w_hi, 1. / w_lo, n_w)
+            omega = 1. / Args['wavelengths']
+            break
+        if feature == 'logGrid':
+            step = np.log(w_hi / w_lo) / (n_w - 1.0)
+            omega = w_lo * np.exp(step * np.arange(n_w))
+            break
+    Args['omega'] = omega.astype(dtype)
+    Args['dw'] = np.abs(np.diff(omega)) if n_w > 1 else np.array([1.], dtype=dtype)
+
+    lo2, hi2 = Args['grid'][1]
+    p_lo, p_hi = Args['grid'][2]
+    axis2 = np.linspace(lo2, hi2, n_2)
+    phi = p_lo + (p_hi - p_lo) / n_p * np.arange(n_p)      # end point excluded
+    far = Args['mode'] == 'far'
+    unit = dtype(1.) if far else 1.
+    d2 = axis2[1] - axis2[0] if n_2 > 1 else unit
+    Args['dph'] = phi[1] - phi[0] if n_p > 1 else unit
+    Args['phi'] = phi.astype(dtype)
+    if far:
+        Args['dth'] = d2
+        Args['theta'] = axis2.astype(dtype)
+    else:
+        Args['dr'] = d2
+        Args['radius'] = axis2.astype(dtype)
+    Args['dV'] = Args['dw'] * d2 * Args['dph']
+    return Args, dtype
+
+
+def omega_is_uniform(Args):
+    """True when the omega axis is the default ascending linspace (phasor recurrence allowed)."""
+    feats = Args.get('Features', [])
+    return not any(f in ('wavelengthGrid', 'logGrid') for f in feats) and \
+        int(Args['gridNodeNums'][0]) >= 2 and Args['grid'][0][1] > Args['grid'][0][0]
+
+
+def grid_tables(Args, dtype):
+    """The arrays the kernels read, in the compute dtype: omega is pre-multiplied by 2*pi in
+    dtype precision (calc.py:494-495); sin/cos are taken of the dtype-cast axes."""
+    T = {'omega': np.ascontiguousarray(dtype(2 * np.pi) * Args['omega']),
+         'sinPhi': np.ascontiguousarray(np.sin(Args['phi'])),
+         'cosPhi': np.ascontiguousarray(np.cos(Args['phi']))}
+    if Args['mode'] == 'far':
+        T['sinTheta'] = np.ascontiguousarray(np.sin(Args['theta']))
+        T['cosTheta'] = np.ascontiguousarray(np.cos(Args['theta']))
+    else:
+        T['radius'] = np.ascontiguousarray(Args['radius'])
+    return T
+
+
+def form_factor(Args, dtype):
+    """Gaussian particle form factor exp(-(2 pi omega sigma)^2 / 2) (calc.py:475-478)."""
+    e = dtype(-0.5) * (dtype(2 * np.pi) * Args['omega'] * Args['sigma_particle']) ** 2
+    return np.ascontiguousarray(np.exp(e).astype(dtype))
+
+
+def snap_iterations(it_range, nSnaps):
+    return np.ascontiguousarray(
+        np.linspace(it_range[0], it_range[1], int(nSnaps) + 1, dtype=np.uint32)[1:])
+
+
+def select_tracks(n_available, Np_max, rank, size):
+    """Indices of the tracks this rank integrates: the first min(Np_max, N) tracks,
+    round-robin over ranks (calc.py:204-212, 230-236)."""
+    n = n_available if Np_max is None else min(int(Np_max), n_available)
+    return np.arange(n)[rank::size]
+
+
+def normalized_weights(weights, mode):
+    """weights_normalize of calc.py:241-263, on the RANK-LOCAL list (Q7)."""
+    w = np.asarray(weights, dtype=np.double)
+    if mode == 'mean':
+        return w / np.mean(w) if w.size else w
+    if mode == 'max':
+        return w / np.max(w) if w.size else w
+    if mode == 'ones':
+        return np.ones_like(w)
+    return w
+
+
+class PackedTracks:
+    """All tracks of a rank in the C-ABI layout (host arrays; `alloc` decides where they live)."""
+    __slots__ = ('n', 'coords', 'offsets', 'w', 'itStart', 'itEnd', 'itSnaps', 'snapStride',
+                 'total', 'updates_per_node')
+
+
+def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
+    """Concatenate tracks into SoA arrays of the compute dtype.
+
+    tracks : list of [x, y, z, ux, uy, uz, w(, it_start)] (calc.py:110-116)
+    weights: per-track weights after normalisation
+    it_range None -> per track it_start=0, it_range=(0, n), own snapshot row (calc.py:297-301)
+    alloc(shape, dtype) -> writable ndarray (e.g. a view of a pinned torch tensor)
+    """
+    if alloc is None:
+        alloc = lambda shape, dt: np.empty(shape, dtype=dt)
+    n = len(tracks)
+    lens = np.fromiter((np.asarray(t[0]).size for t in tracks), dtype=np.uint64, count=n)
+    P = PackedTracks()
+    P.n = n
+    P.offsets = alloc((n + 1,), np.uint64)
+    P.offsets[0] = 0
+    np.cumsum(lens, out=P.offsets[1:])
+    P.total = int(P.offsets[n])
+    P.coords = [alloc((max(P.total, 1),), dtype) for _ in range(6)]
+    P.w = alloc((max(n, 1),), dtype)
+    P.itStart = alloc((max(n, 1),), np.uint32)
+    P.itEnd = alloc((max(n, 1),), np.uint32)
+    nSnaps = int(nSnaps)
+    if it_range is None:
+        P.snapStride = nSnaps
+        P.itSnaps = alloc((max(n, 1), nSnaps), np.uint32)
+    else:
+        P.snapStride = 0
+        P.itSnaps = alloc((nSnaps,), np.uint32)
+        P.itSnaps[:] = snap_iterations(it_range, nSnaps)
+    upd = 0
+    for i, t in enumerate(tracks):
+        o, e = int(P.offsets[i]), int(P.offsets[i + 1])
+        for c in range(6):
+            a = np.asarray(t[c])
+            if a.size != e - o:
+                raise ValueError(f'track {i}: coordinate arrays differ in length')
+            P.coords[c][o:e] = a            # astype(dtype) happens in the assignment
+        P.w[i] = weights[i]
+        m = e - o
+        if it_range is None:
+            P.itStart[i] = 0
+            P.itEnd[i] = m
+            P.itSnaps[i, :] = snap_iterations((0, m), nSnaps)
+            end = m
+        else:
+            P.itStart[i] = t[7] if len(t) == 8 else 0
+            P.itEnd[i] = it_range[-1]
+            end = int(it_range[-1])
+        upd += max(0, min(m - 1, end - 1))
+    P.updates_per_node = upd
+    return P

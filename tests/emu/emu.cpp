@@ -1,0 +1,75 @@
+// TEST INFRASTRUCTURE ONLY — single-warp CPU emulation of the device code in
+// synchrad_b200/csrc/srb_core.cuh (lanes run as a loop, shared memory is a plain struct).
+// It exists so the kernel LOGIC (flush chains, pass ranges, seeds, recurrences, tile indexing)
+// can be debugged against the oracle in a container without a GPU.  It is not a fallback: the
+// product package never loads it and fails loudly without the CUDA library.
+// Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC -o tests/emu/libsrb_emu.so tests/emu/emu.cpp
+#include <cstring>
+#include <vector>
+
+#include "../../include/synchrad_b200.h"
+#include "../../synchrad_b200/csrc/srb_core.cuh"
+
+using namespace srb;
+
+template <class C>
+static void run_all(const Params& P0, unsigned long long* counters) {
+  unsigned long long tot[2] = {0, 0};
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : tot[:2])
+  for (long long task = 0; task < (long long)P0.nVD * P0.nPC; task++) {
+    Params P = P0;
+    unsigned long long cnt[2] = {0, 0};
+    P.counters = cnt;
+    const uint32_t vd = (uint32_t)(task % P0.nVD), pc = (uint32_t)(task / P0.nVD);
+    WarpSmem<C> sm;
+    ThreadState<C> st[32];
+    std::memset(&sm, 0, sizeof sm);
+    warp_task<C>(P, vd, pc, sm, st);
+    tot[0] += cnt[0]; tot[1] += cnt[1];
+  }
+  if (counters) { counters[0] = tot[0]; counters[1] = tot[1]; }
+}
+
+extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int nOut,
+                                 int kind, int tw, uint32_t nPC, unsigned long long* counters) {
+  Params P;
+  std::memset(&P, 0, sizeof P);
+  P.mode = g->mode; P.comp = g->comp;
+  P.nOmega = g->nOmega; P.nA2 = g->nAxis2; P.nPhi = g->nPhi; P.nSnaps = g->nSnaps;
+  P.omega = g->omega;
+  P.axA = g->mode == SRB_MODE_FAR ? g->sinTheta : g->radius;
+  P.axB = g->mode == SRB_MODE_FAR ? g->cosTheta : nullptr;
+  P.sinPhi = g->sinPhi; P.cosPhi = g->cosPhi; P.formFactor = g->formFactor;
+  P.L = g->L_screen; P.dt = g->dt;
+  P.descending = g->omega_last_host < g->omega_first_host ? 1 : 0;
+  P.domega = g->nOmega > 1 ? (g->omega_last_host - g->omega_first_host) / (double)(g->nOmega - 1) : 0.0;
+  const int tiles = kind == KIND_RECUR ? 16 : 32;
+  P.chunkNodes = (uint32_t)(tiles * tw);
+  P.nChunks = (g->nOmega + P.chunkNodes - 1) / P.chunkNodes;
+  P.nVD = g->nPhi * g->nAxis2 * P.nChunks;
+  P.nTracks = t->nTracks;
+  P.x = t->x; P.y = t->y; P.z = t->z; P.ux = t->ux; P.uy = t->uy; P.uz = t->uz;
+  P.offsets = t->offsets; P.w = t->w; P.itStart = t->itStart; P.itEnd = t->itEnd; P.itSnaps = t->itSnaps;
+  P.snapStride = t->itSnapsStride;
+  for (int c = 0; c < nOut; c++) P.out[c] = spectra[c];
+  const size_t perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
+  std::vector<double> slabs((size_t)(nPC > 1 ? nPC - 1 : 0) * perOut * nOut, 0.0);
+  P.slabs = slabs.data(); P.slabStride = perOut * nOut; P.nPC = nPC;
+  const bool f32 = g->dtype == SRB_DTYPE_F32;
+  bool ok = false;
+#define EMU_CASE(K, M, TWV)                                                                     \
+  if (kind == K && g->mode == M && tw == TWV) {                                                 \
+    if (f32) run_all<Cfg<float, float, M, K, TWV, false>>(P, counters);                         \
+    else run_all<Cfg<double, double, M, K, TWV, false>>(P, counters);                           \
+    ok = true; }
+  EMU_CASE(KIND_RECUR, MODE_FAR, 16) EMU_CASE(KIND_RECUR, MODE_FAR, 8) EMU_CASE(KIND_RECUR, MODE_FAR, 4)
+  EMU_CASE(KIND_RECUR, MODE_NEAR, 8) EMU_CASE(KIND_RECUR, MODE_NEAR, 4) EMU_CASE(KIND_RECUR, MODE_NEAR, 2)
+  EMU_CASE(KIND_DIRECT, MODE_FAR, 8) EMU_CASE(KIND_DIRECT, MODE_FAR, 4) EMU_CASE(KIND_DIRECT, MODE_FAR, 2)
+  EMU_CASE(KIND_DIRECT, MODE_NEAR, 8) EMU_CASE(KIND_DIRECT, MODE_NEAR, 4) EMU_CASE(KIND_DIRECT, MODE_NEAR, 2)
+#undef EMU_CASE
+  if (!ok) return -1;
+  for (uint32_t s = 0; s + 1 < nPC; s++)
+    for (int c = 0; c < nOut; c++)
+      for (size_t i = 0; i < perOut; i++) P.out[c][i] += slabs[(size_t)s * P.slabStride + (size_t)c * perOut + i];
+  return 0;
+}

@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY — drives the single-warp CPU emulation of the device code
+(tests/emu/emu.cpp) through the SAME host packing the product uses, so kernel logic can be
+checked against the oracle without a GPU.  Never imported by the product."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from synchrad_b200 import _lib, host
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, 'libsrb_emu.so')
+_SRC = [os.path.join(_HERE, 'emu.cpp'),
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh')]
+
+
+def build():
+    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in _SRC):
+        return
+    subprocess.check_call(['/usr/bin/g++', '-std=c++17', '-O2', '-ffp-contract=off', '-fopenmp',
+                           '-shared', '-fPIC', '-o', _SO, _SRC[0]])
+
+
+def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSnaps=1,
+        sigma_particle=0, kind='recur', tw=None, nPC=1):
+    """Returns (radiation dict in host layout, counters)."""
+    build()
+    lib = ctypes.CDLL(_SO)
+    A = dict(Args)
+    A, dtype = host.init_args(A)
+    A['sigma_particle'] = dtype(sigma_particle)
+    if A['mode'] == 'near':
+        A['L_screen'] = L_screen
+    A['timeStep'] = dtype(timeStep)
+    T = host.grid_tables(A, dtype)
+    weights = [t[6] for t in tracks]
+    pk = host.pack_tracks(tracks, weights, dtype, it_range, nSnaps)
+    n_w, n_2, n_p = (int(v) for v in A['gridNodeNums'])
+    g = _lib.srb_grid()
+    g.mode, g.comp = _lib.MODE[A['mode']], _lib.COMP[comp]
+    g.dtype = 0 if dtype is np.double else 1
+    g.omega_uniform = 1 if host.omega_is_uniform(A) else 0
+    g.nOmega, g.nAxis2, g.nPhi, g.nSnaps = n_w, n_2, n_p, nSnaps
+    g.omega = T['omega'].ctypes.data
+    g.sinPhi, g.cosPhi = T['sinPhi'].ctypes.data, T['cosPhi'].ctypes.data
+    if A['mode'] == 'far':
+        g.sinTheta, g.cosTheta = T['sinTheta'].ctypes.data, T['cosTheta'].ctypes.data
+    else:
+        g.radius = T['radius'].ctypes.data
+        g.L_screen = float(dtype(L_screen))
+    ff = host.form_factor(A, dtype)
+    g.formFactor = ff.ctypes.data
+    g.dt = float(dtype(timeStep))
+    g.omega_first_host, g.omega_last_host = float(T['omega'][0]), float(T['omega'][-1])
+    t = _lib.srb_tracks()
+    t.nTracks = pk.n
+    for nm, a in zip(('x', 'y', 'z', 'ux', 'uy', 'uz'), pk.coords):
+        setattr(t, nm, a.ctypes.data)
+    t.offsets, t.w = pk.offsets.ctypes.data, pk.w.ctypes.data
+    t.itStart, t.itEnd, t.itSnaps = pk.itStart.ctypes.data, pk.itEnd.ctypes.data, pk.itSnaps.ctypes.data
+    t.itSnapsStride, t.totalSteps_host = pk.snapStride, pk.total
+    keys = host.COMP_KEYS[comp]
+    spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
+    sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
+    kind_i = 1 if kind == 'recur' else 0
+    if tw is None:
+        tiles = 16 if kind_i else 32
+        opts = ([4, 8, 16] if A['mode'] == 'far' else [2, 4, 8]) if kind_i else [2, 4, 8]
+        tw = next((o for o in opts if tiles * o >= n_w), opts[-1])
+    cnt = (ctypes.c_ulonglong * 2)(0, 0)
+    lib.srb_emu_integrate.restype = ctypes.c_int
+    rc = lib.srb_emu_integrate(ctypes.byref(g), ctypes.byref(t), sp, len(keys), kind_i, int(tw),
+                               ctypes.c_uint32(nPC), cnt)
+    assert rc == 0, 'emulator has no such configuration'
+    rad = {k: np.ascontiguousarray(s.swapaxes(-1, -3)) for k, s in zip(keys, spectra)}
+    return rad, (cnt[0], cnt[1])
