@@ -42,7 +42,12 @@ extern "C" {
 #define SRB_COMP_SPHERIC 3           /* spheric_comps (far only) -> 3 spectra   */
 #define SRB_COMP_SPHERIC_COMPLEX 4   /* spheric_comps_complex    -> 6 spectra   */
 
-/* dtype: the Mako variable `my_dtype` (calc.py:610-611) */
+/* dtype: the Mako variable `my_dtype` (calc.py:610-611).
+ * F64: everything in double, bit-faithful to the strict reading of the reference kernels.
+ * F32: MIXED precision — tables, tracks and all per-(direction, step) work stay float64; only
+ *      the per-omega phasor and accumulation arithmetic is float32.  (The reference's literal
+ *      float32 path loses ~0.4 rad of phase to the float32 rounding of tracks and direction
+ *      cosines alone; it has no reproducible answer to be bit-compatible with.) */
 #define SRB_DTYPE_F64 0
 #define SRB_DTYPE_F32 1
 
@@ -52,8 +57,8 @@ extern "C" {
 #define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
 
 /* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
- * Tables are in the compute dtype, exactly as `_init_data` uploads them (calc.py:486-512):
- * omega is already multiplied by 2*pi. */
+ * Tables are float64 arrays with the content `_init_data` uploads (calc.py:486-512): omega is
+ * already multiplied by 2*pi. */
 typedef struct srb_grid {
   int32_t mode;    /* SRB_MODE_*  */
   int32_t comp;    /* SRB_COMP_*  */
@@ -63,16 +68,16 @@ typedef struct srb_grid {
   int32_t omega_uniform; /* host hint: table is an ascending uniform grid (no Features) */
   uint32_t nOmega, nAxis2, nPhi; /* `gridNodeNums`; nAxis2 = nTheta (far) | nRadius (near) */
   uint32_t nSnaps;
-  const void* omega;      /* [nOmega]  2*pi*omega            */
-  const void* sinTheta;   /* [nAxis2]  far                   */
-  const void* cosTheta;   /* [nAxis2]  far                   */
-  const void* radius;     /* [nAxis2]  near                  */
-  const void* sinPhi;     /* [nPhi]                          */
-  const void* cosPhi;     /* [nPhi]                          */
-  const void* formFactor; /* [nOmega] or NULL; applied by far cartesian_complex only,
+  const double* omega;      /* [nOmega]  2*pi*omega            */
+  const double* sinTheta;   /* [nAxis2]  far                   */
+  const double* cosTheta;   /* [nAxis2]  far                   */
+  const double* radius;     /* [nAxis2]  near                  */
+  const double* sinPhi;     /* [nPhi]                          */
+  const double* cosPhi;     /* [nPhi]                          */
+  const double* formFactor; /* [nOmega] or NULL; applied by far cartesian_complex only,
                              as in the reference (kernel_farfield.cl:271,324-325) */
   double L_screen;        /* near: `distanceToScreen`        */
-  double dt;              /* `timeStep`, already rounded to the compute dtype */
+  double dt;              /* `timeStep` (c*dt)               */
   double omega_first_host, omega_last_host; /* host copies of omega[0], omega[nOmega-1] */
 } srb_grid;
 
@@ -80,9 +85,9 @@ typedef struct srb_grid {
  * every particle at once.  Track t occupies [offsets[t], offsets[t+1]) of each coordinate array. */
 typedef struct srb_tracks {
   uint32_t nTracks;
-  const void *x, *y, *z, *ux, *uy, *uz; /* compute dtype */
+  const double *x, *y, *z, *ux, *uy, *uz;
   const uint64_t* offsets;              /* [nTracks+1] */
-  const void* w;                        /* [nTracks] compute dtype: `wp` */
+  const double* w;                      /* [nTracks] `wp` */
   const uint32_t* itStart;              /* [nTracks] */
   const uint32_t* itEnd;                /* [nTracks] `np.uint32(it_range[-1])` (calc.py:307) */
   const uint32_t* itSnaps;              /* snapshot iterations (calc.py:626-630) */
@@ -135,6 +140,11 @@ typedef struct srb_launch_info {
   uint32_t kernels_launched;
 } srb_launch_info;
 int srb_last_launch(srb_launch_info* info);
+
+/* Measured issue-limited peak of one pipe on the current device, in lane-operations per second:
+ * which = 0 FP64 FMA, 1 FP32 FMA, 2 MUFU (sin.approx).  Runs a ~50 ms micro-kernel; synchronous.
+ * These are the denominators of the compute roofline (the path is issue-bound, not HBM-bound). */
+int srb_pipe_peak(int which, double* ops_per_second);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,8 @@ PHASOR = {'auto': 0, 'direct': 1, 'recur': 2}
 
 # every symbol include/synchrad_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ('srb_version', 'srb_last_error', 'srb_num_spectra', 'srb_scratch_bytes',
-           'srb_integrate', 'srb_integrate_host', 'srb_swap_axes', 'srb_last_launch')
+           'srb_integrate', 'srb_integrate_host', 'srb_swap_axes', 'srb_last_launch',
+           'srb_pipe_peak')
 
 
 class srb_grid(ctypes.Structure):
@@ -89,6 +90,8 @@ def load():
     lib.srb_swap_axes.restype = ctypes.c_int
     lib.srb_swap_axes.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_uint32] * 4 \
         + [ctypes.c_void_p]
+    lib.srb_pipe_peak.restype = ctypes.c_int
+    lib.srb_pipe_peak.argtypes = [ctypes.c_int, P(ctypes.c_double)]
     lib.srb_last_launch.restype = ctypes.c_int
     lib.srb_last_launch.argtypes = [P(srb_launch_info)]
     _lib = lib

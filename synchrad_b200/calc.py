@@ -150,6 +150,7 @@ class SynchRad(Utilities):
             self.Args['theta'] = np.arctan2(self.Args['radius'], self.Args['L_screen'])
         if timeStep is not None:
             self.Args['timeStep'] = self.dtype(timeStep)
+            self._timeStep64 = float(timeStep)
         if it_range is not None:
             it_range = tuple(int(v) for v in it_range)
 
@@ -157,6 +158,7 @@ class SynchRad(Utilities):
             from . import trackio
             cdt, file_range, n_file = trackio.read_header(file_tracks)
             self.Args['timeStep'] = self.dtype(cdt)
+            self._timeStep64 = float(cdt)
             if it_range is None:
                 if file_range is not None:
                     it_range = tuple(int(v) for v in file_range)
@@ -168,6 +170,8 @@ class SynchRad(Utilities):
             particleTracks = trackio.read_tracks(file_tracks, index)
             if self.rank == 0 and verbose:
                 print('Tracks are loaded')
+        elif isinstance(particleTracks, host.PackedTracks):
+            pass      # extension: this rank's tracks already in the C-ABI layout (host.pack_tracks)
         else:
             if it_range is None and self.rank == 0 and verbose:
                 print('Separate it_range for each track will be used')
@@ -178,21 +182,29 @@ class SynchRad(Utilities):
         if it_range is not None:
             self._set_snap_iterations(it_range, nSnaps)
 
-        weights = host.normalized_weights([t[6] for t in particleTracks], weights_normalize)
-        for t, w in zip(particleTracks, weights):       # the reference mutates the track list
-            if weights_normalize in ('mean', 'max', 'ones') and isinstance(t, list):
-                t[6] = float(w)
-        self.total_weight = float(np.sum(weights)) if len(weights) else 0.0
-
-        alloc = engine.PinnedAlloc()
-        packed = host.pack_tracks(particleTracks, weights, self.dtype, it_range, nSnaps, alloc)
+        if isinstance(particleTracks, host.PackedTracks):
+            packed = particleTracks
+            if weights_normalize is not None or Np_max is not None:
+                raise ValueError('pre-packed tracks: normalise weights / select tracks before packing')
+            if (packed.snapStride == 0) != (it_range is not None) or packed.itSnaps.shape[-1] != nSnaps:
+                raise ValueError('pre-packed tracks were packed for a different it_range / nSnaps')
+            self.total_weight = float(np.sum(packed.w[:packed.n]))
+        else:
+            weights = host.normalized_weights([t[6] for t in particleTracks], weights_normalize)
+            for t, w in zip(particleTracks, weights):       # the reference mutates the track list
+                if weights_normalize in ('mean', 'max', 'ones') and isinstance(t, list):
+                    t[6] = float(w)
+            self.total_weight = float(np.sum(weights)) if len(weights) else 0.0
+            alloc = engine.PinnedAlloc()
+            packed = host.pack_tracks(particleTracks, weights, np.double, it_range, nSnaps, alloc)
         if it_range is None and packed.n:
             self.snap_iterations = np.array(packed.itSnaps[packed.n - 1])   # last track's, as in the reference
         elif it_range is None:
             self.snap_iterations = np.zeros(nSnaps, dtype=np.uint32)
 
         res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
-                               native=self._native, phasor=self._phasor)
+                               native=self._native, phasor=self._phasor,
+                               timeStep=getattr(self, '_timeStep64', float(self.Args['timeStep'])))
         n_w, n_2, n_p = (int(v) for v in self.Args['gridNodeNums'])
         dev_out = engine.to_host_layout(res.spectra, nSnaps, n_w, n_2, n_p)
         keys = host.COMP_KEYS[comp]

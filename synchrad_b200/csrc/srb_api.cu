@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -62,6 +63,26 @@ __global__ void k_swap_axes(const double* __restrict__ src, double* __restrict__
   }
 }
 
+// Issue-rate micro-kernels: the denominators of the compute roofline, measured on
+// the device the benchmark runs on.  8 independent FMA chains per thread, 16 warps per SM.
+template <typename T, bool MUFU>
+__global__ void k_pipe_peak(T* out, T a, T b, int iters) {
+  T v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (T)threadIdx.x * (T)1e-3 + (T)i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (MUFU) v[i] = (T)__sinf((float)v[i]);
+      else v[i] = fma(v[i], a, b);
+    }
+  }
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += v[i];
+  if (s == (T)123.456) out[0] = s;
+}
+
 struct Launcher {
   void (*kernel)(const srb::Params);
   size_t smem;
@@ -83,16 +104,16 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, Launcher* L) {
   SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 16, double, double)
   SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 8, double, double)
   SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 4, double, double)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 16, float, float)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 8, float, float)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 4, float, float)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 16, double, float)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 8, double, float)
+  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 4, double, float)
   // recurrence, near
   SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 8, double, double)
   SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 4, double, double)
   SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 2, double, double)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 8, float, float)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 4, float, float)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 2, float, float)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 8, double, float)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 4, double, float)
+  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 2, double, float)
   // direct
   SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 8, double, double)
   SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 4, double, double)
@@ -100,18 +121,18 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, Launcher* L) {
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 8, double, double)
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 4, double, double)
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 2, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 8, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 4, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 2, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 8, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 4, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 2, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 8, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 4, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, float, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, float, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 8, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 4, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 2, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 8, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 4, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 2, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 8, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 4, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, double, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, double, float)
 #undef SRB_CASE
   return false;
 }
@@ -152,6 +173,12 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
   if (g->phasor == SRB_PHASOR_RECUR && !uniform) return fail("phasor recurrence needs an ascending uniform omega grid");
   p->kind = (g->phasor == SRB_PHASOR_DIRECT || !uniform) ? KIND_DIRECT : KIND_RECUR;
+  // near field: phase = omega*(t+R) ~ omega*L.  Beyond 2^18 rad the recurrence cannot track the
+  // reference's rounded phase to 1e-9 (srb_core.cuh, flag 3), every step would fall back, so the
+  // direct kernel (full lane layout) is chosen outright.
+  if (g->phasor == SRB_PHASOR_AUTO && g->mode == SRB_MODE_NEAR && g->dtype == SRB_DTYPE_F64 &&
+      std::fabs(g->omega_last_host * g->L_screen) > 262144.0)
+    p->kind = KIND_DIRECT;
   p->native = (p->kind == KIND_DIRECT && g->dtype == SRB_DTYPE_F32 && g->native != 0);   // Q9
   const int tiles = p->kind == KIND_RECUR ? 16 : 32;
   int twMax, twMin;
@@ -265,6 +292,34 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   return 0;
 }
 
+int srb_pipe_peak(int which, double* ops_per_second) {
+  if (!ops_per_second) return fail("null result pointer");
+  int dev = 0, numSM = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev));
+  void* buf = nullptr;
+  SRB_CUDA(cudaMalloc(&buf, 64));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 40000, blocks = numSM * 2, threads = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    if (which == 0) k_pipe_peak<double, false><<<blocks, threads>>>((double*)buf, 1.0000001, 1e-9, iters);
+    else if (which == 1) k_pipe_peak<float, false><<<blocks, threads>>>((float*)buf, 1.0000001f, 1e-9f, iters);
+    else k_pipe_peak<float, true><<<blocks, threads>>>((float*)buf, 1.0f, 0.0f, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  SRB_CUDA(cudaGetLastError());
+  *ops_per_second = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+  return 0;
+}
+
 int srb_last_launch(srb_launch_info* info) {
   if (!info) return fail("null info");
   *info = g_info;
@@ -290,7 +345,7 @@ int srb_integrate_host(const srb_grid* g, const srb_tracks* t, double* const* sp
   SRB_CUDA(cudaSetDevice(device));
   const int nOut = srb_num_spectra(g->mode, g->comp);
   if (n_spectra != nOut || !spectra) return fail("n_spectra does not match comp");
-  const size_t es = g->dtype == SRB_DTYPE_F64 ? 8 : 4;
+  const size_t es = 8;   // tables and tracks are float64 for both dtypes
   std::vector<void*> owned;
   auto cleanup = [&]() { for (void* q : owned) cudaFree(q); };
   cudaError_t err = cudaSuccess;
@@ -304,16 +359,16 @@ int srb_integrate_host(const srb_grid* g, const srb_tracks* t, double* const* sp
     return d;
   };
   srb_grid gd = *g; srb_tracks td = *t;
-  gd.omega = up(g->omega, g->nOmega * es);
-  gd.sinTheta = up(g->sinTheta, g->nAxis2 * es); gd.cosTheta = up(g->cosTheta, g->nAxis2 * es);
-  gd.radius = up(g->radius, g->nAxis2 * es);
-  gd.sinPhi = up(g->sinPhi, g->nPhi * es); gd.cosPhi = up(g->cosPhi, g->nPhi * es);
-  gd.formFactor = up(g->formFactor, g->nOmega * es);
+  gd.omega = (const double*)up(g->omega, g->nOmega * es);
+  gd.sinTheta = (const double*)up(g->sinTheta, g->nAxis2 * es); gd.cosTheta = (const double*)up(g->cosTheta, g->nAxis2 * es);
+  gd.radius = (const double*)up(g->radius, g->nAxis2 * es);
+  gd.sinPhi = (const double*)up(g->sinPhi, g->nPhi * es); gd.cosPhi = (const double*)up(g->cosPhi, g->nPhi * es);
+  gd.formFactor = (const double*)up(g->formFactor, g->nOmega * es);
   const uint64_t total = t->totalSteps_host;
-  td.x = up(t->x, total * es); td.y = up(t->y, total * es); td.z = up(t->z, total * es);
-  td.ux = up(t->ux, total * es); td.uy = up(t->uy, total * es); td.uz = up(t->uz, total * es);
+  td.x = (const double*)up(t->x, total * es); td.y = (const double*)up(t->y, total * es); td.z = (const double*)up(t->z, total * es);
+  td.ux = (const double*)up(t->ux, total * es); td.uy = (const double*)up(t->uy, total * es); td.uz = (const double*)up(t->uz, total * es);
   td.offsets = (const uint64_t*)up(t->offsets, (size_t)(t->nTracks + 1) * 8);
-  td.w = up(t->w, t->nTracks * es);
+  td.w = (const double*)up(t->w, t->nTracks * es);
   td.itStart = (const uint32_t*)up(t->itStart, (size_t)t->nTracks * 4);
   td.itEnd = (const uint32_t*)up(t->itEnd, (size_t)t->nTracks * 4);
   td.itSnaps = (const uint32_t*)up(t->itSnaps, (size_t)(t->itSnapsStride ? (size_t)t->nTracks * g->nSnaps : g->nSnaps) * 4);

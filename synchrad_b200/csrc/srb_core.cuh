@@ -99,7 +99,23 @@ SRB_HD void sincos_d(double x, double* s, double* c) {
   *s = sin(x); *c = cos(x);
 #endif
 }
-SRB_HD void sincos_t(double x, double* s, double* c) { sincos_d(x, s, c); }
+// sin/cos of a double of ANY magnitude at fast-path cost: x/pi is formed as an exact
+// double-double product, reduced mod 2 exactly, and handed to sincospi (whose own reduction is
+// exact).  Near-field phases omega*(t+R) reach 1e10 rad and SI-unit far-field phases 1e6
+// (SURVEY §7), far beyond the fast path of CUDA's sincos().  Absolute phase error ~1e-15 rad.
+SRB_HD void sincos_big(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  const double h = __dmul_rn(x, 0.3183098861837907);
+  double l = __fma_rn(x, 0.3183098861837907, -h);
+  l = __fma_rn(x, -1.9678676675182486e-17, l);
+  const double n = __dsub_rn(__fma_rn(h, 0.5, 6755399441055744.0), 6755399441055744.0);  // rint(h/2)
+  const double f = __dadd_rn(__fma_rn(n, -2.0, h), l);
+  sincospi(f, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+SRB_HD void sincos_t(double x, double* s, double* c) { sincos_big(x, s, c); }
 SRB_HD double tmul(double a, double b) { return smul(a, b); }
 SRB_HD float tmul(float a, float b) {
 #if defined(__CUDA_ARCH__)
@@ -300,8 +316,8 @@ SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& 
   using TI = typename C::TI; using TM = typename C::TM;
   const double w0 = (double)((const TI*)P.omega)[g.cLo];
   double s0, c0, sd, cd;
-  sincos_d(smul(w0, tau), &s0, &c0);
-  sincos_d(P.domega * tau, &sd, &cd);
+  sincos_big(smul(w0, tau), &s0, &c0);
+  sincos_big(P.domega * tau, &sd, &cd);
   coef = 2.0 * cd;
   double cw = cd, sw = sd;
 #pragma unroll
@@ -333,11 +349,18 @@ SRB_HD void prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint
   uint32_t lo, hi;
   pass_range<C>(P, g, tau, tauPrev, lo, hi);
   const uint32_t n = g.cHi - g.cLo;
-  const uint32_t flag = (hi <= lo) ? 0u : ((lo == 0 && hi == n) ? 1u : 2u);
+  uint32_t flag = (hi <= lo) ? 0u : ((lo == 0 && hi == n) ? 1u : 2u);
+  double last = tau;
+  if (C::KIND == KIND_RECUR && flag) {
+    // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
+    // beyond |phase| ~ 2^18 that exceeds the 1e-9 parity budget, so such steps are evaluated
+    // node by node (flag 3).  fp32 main phase: the seeds are fp64, no such limit.
+    const double wl = (double)((const typename C::TI*)P.omega)[P.descending ? g.cLo : g.cHi - 1];
+    const bool big = sizeof(TM) == 8 && fabs(wl * tau) > 262144.0;
+    if (big) flag = 3u; else make_seeds<C>(P, g, tau, sm, lane, last);
+  }
   sm.rng[lane] = lo | (hi << 10) | (flag << 30);
   st.nPass += hi - lo; st.nAll += n;
-  double last = tau;
-  if (C::KIND == KIND_RECUR && flag) make_seeds<C>(P, g, tau, sm, lane, last);
   constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
 #pragma unroll
   for (int k = 0; k < NV; k++) sm.rec[lane][k] = (TM)V[k];
@@ -346,8 +369,9 @@ SRB_HD void prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint
 
 // -------------------------------------------------------------------------------- main phase
 template <class C>
-SRB_HD void main_recur(const WarpSmem<C>& sm, int cnt, int lane, ThreadState<C>& st) {
-  using TM = typename C::TM;
+SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, int lane,
+                       ThreadState<C>& st) {
+  using TM = typename C::TM; using TI = typename C::TI;
   constexpr int TW = C::TW;
   constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
   const int m = lane & 15;
@@ -359,6 +383,23 @@ SRB_HD void main_recur(const WarpSmem<C>& sm, int cnt, int lane, ThreadState<C>&
 #pragma unroll
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
     const TM coef = sm.rec[s][NV];
+    if (flag == 3) {   // direct evaluation of this step (phase too large for the recurrence)
+      const int lo = (int)(r & 0x3ffu) - m * TW, hi = (int)((r >> 10) & 0x3ffu) - m * TW;
+      if (hi <= 0 || lo >= TW) continue;
+      const uint32_t j0 = g.cLo + (uint32_t)(m * TW);
+      for (int k = (lo > 0 ? lo : 0); k < (hi < TW ? hi : TW); k++) {
+        TM sn, cs;
+        sincos_t(tmul((TM)((const TI*)P.omega)[j0 + k], coef), &sn, &cs);   // coef slot holds tau
+        const TM cur = (lane >> 4) ? sn : cs;
+#pragma unroll
+        for (int kk = 0; kk < TW; kk++)
+          if (kk == k) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) st.acc[kk * NV + c] = fma(V[c], cur, st.acc[kk * NV + c]);
+          }
+      }
+      continue;
+    }
     TM vm = sm.seeds[lane][s], v = sm.seeds[32 + lane][s];
     if (flag == 1) {
 #pragma unroll
@@ -600,7 +641,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
           prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);
         SRB_LANES_END
         SRB_LANES_BEGIN
-          if (C::KIND == KIND_RECUR) main_recur<C>(sm, cnt, lane, SRB_ST);
+          if (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, lane, SRB_ST);
         SRB_LANES_END
       }

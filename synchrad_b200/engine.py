@@ -50,7 +50,7 @@ class DeviceGrid:
     def __init__(self, Args, dtype, device):
         self.device = device
         self.dtype = dtype
-        self.host = host.grid_tables(Args, dtype)
+        self.host = host.grid_tables(Args)
         self.dev = {k: torch.from_numpy(v).to(device) for k, v in self.host.items()}
         self.uniform = host.omega_is_uniform(Args)
 
@@ -60,7 +60,7 @@ class Result:
 
 
 def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='auto',
-              counters=True, device_tracks=None, timing=False):
+              counters=True, device_tracks=None, timing=False, timeStep=None):
     """Run the hot path for the packed tracks of this rank.
 
     Returns Result with `spectra`: list of float64 device tensors (nSnaps, nPhi, nAxis2, nOmega).
@@ -92,7 +92,7 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
             n_tracks, total, stride = d['n'], d['total'], d['snapStride']
         ff = None
         if comp == 'cartesian_complex' and mode == 'far':
-            ff = torch.from_numpy(host.form_factor(Args, dtype)).to(dev)
+            ff = torch.from_numpy(host.form_factor(Args)).to(dev)
 
         g = _lib.srb_grid()
         g.mode, g.comp, g.dtype = _lib.MODE[mode], _lib.COMP[comp], _lib.DTYPE[
@@ -108,9 +108,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
             g.sinTheta, g.cosTheta = T['sinTheta'].data_ptr(), T['cosTheta'].data_ptr()
         else:
             g.radius = T['radius'].data_ptr()
-            g.L_screen = float(dtype(Args['L_screen']))
+            g.L_screen = float(Args['L_screen'])
         g.formFactor = ff.data_ptr() if ff is not None else None
-        g.dt = float(dtype(Args['timeStep']))
+        g.dt = float(Args['timeStep']) if (timeStep is None or dtype is np.double) else float(timeStep)
         g.omega_first_host = float(grid.host['omega'][0])
         g.omega_last_host = float(grid.host['omega'][-1])
 

@@ -87,6 +87,20 @@ def init_args(Args):
     return Args, dtype
 
 
+def axes64(Args):
+    """The spectral axes in float64, whatever Args['dtype'] is.  For dtype='double' these are
+    exactly Args['omega'|'theta'|'radius'|'phi']; for 'float' they are the axes BEFORE the
+    reference's cast to float32 (recomputed from Args['grid']), because the device side keeps
+    everything that enters tau = t - n.r in fp64 (see grid_tables)."""
+    if np_dtype(Args['dtype']) is np.double:
+        keys = ('omega', 'phi') + (('theta',) if Args['mode'] == 'far' else ('radius',))
+        return {k: np.asarray(Args[k], dtype=np.double) for k in keys}
+    tmp = {k: Args[k] for k in ('grid', 'mode', 'Features') if k in Args}
+    tmp['dtype'] = 'double'
+    tmp, _ = init_args(tmp)
+    return axes64(tmp)
+
+
 def omega_is_uniform(Args):
     """True when the omega axis is the default ascending linspace (phasor recurrence allowed)."""
     feats = Args.get('Features', [])
@@ -94,24 +108,32 @@ def omega_is_uniform(Args):
         int(Args['gridNodeNums'][0]) >= 2 and Args['grid'][0][1] > Args['grid'][0][0]
 
 
-def grid_tables(Args, dtype):
-    """The arrays the kernels read, in the compute dtype: omega is pre-multiplied by 2*pi in
-    dtype precision (calc.py:494-495); sin/cos are taken of the dtype-cast axes."""
-    T = {'omega': np.ascontiguousarray(dtype(2 * np.pi) * Args['omega']),
-         'sinPhi': np.ascontiguousarray(np.sin(Args['phi'])),
-         'cosPhi': np.ascontiguousarray(np.cos(Args['phi']))}
+def grid_tables(Args, dtype=None):
+    """The float64 arrays the kernels read: omega pre-multiplied by 2*pi (calc.py:494-495),
+    sin/cos of the angular axes (calc.py:498-512).
+
+    dtype='double': bit-identical to what the reference uploads.  dtype='float': the reference
+    would upload float32 tables (and float32 tracks, calc.py:585-597); a float32 n.r alone
+    perturbs the phase by ~0.4 rad on the undulator test (fp32 spectrum 5.7 % of max
+    away from fp64), so this implementation keeps tables, tracks and the per-(direction, step)
+    work in fp64 and runs only the per-omega phasor/accumulate arithmetic in fp32."""
+    ax = axes64(Args)
+    T = {'omega': np.ascontiguousarray(np.double(2 * np.pi) * ax['omega']),
+         'sinPhi': np.ascontiguousarray(np.sin(ax['phi'])),
+         'cosPhi': np.ascontiguousarray(np.cos(ax['phi']))}
     if Args['mode'] == 'far':
-        T['sinTheta'] = np.ascontiguousarray(np.sin(Args['theta']))
-        T['cosTheta'] = np.ascontiguousarray(np.cos(Args['theta']))
+        T['sinTheta'] = np.ascontiguousarray(np.sin(ax['theta']))
+        T['cosTheta'] = np.ascontiguousarray(np.cos(ax['theta']))
     else:
-        T['radius'] = np.ascontiguousarray(Args['radius'])
+        T['radius'] = np.ascontiguousarray(ax['radius'])
     return T
 
 
-def form_factor(Args, dtype):
-    """Gaussian particle form factor exp(-(2 pi omega sigma)^2 / 2) (calc.py:475-478)."""
-    e = dtype(-0.5) * (dtype(2 * np.pi) * Args['omega'] * Args['sigma_particle']) ** 2
-    return np.ascontiguousarray(np.exp(e).astype(dtype))
+def form_factor(Args, dtype=None):
+    """Gaussian particle form factor exp(-(2 pi omega sigma)^2 / 2) (calc.py:475-478), float64."""
+    om = axes64(Args)['omega']
+    e = -0.5 * (2 * np.pi * om * float(Args['sigma_particle'])) ** 2
+    return np.ascontiguousarray(np.exp(e))
 
 
 def snap_iterations(it_range, nSnaps):
@@ -145,7 +167,8 @@ class PackedTracks:
 
 
 def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
-    """Concatenate tracks into SoA arrays of the compute dtype.
+    """Concatenate tracks into SoA arrays of `dtype` (the product always packs float64: see
+    grid_tables for why the reference's astype(float32) is not reproduced in 'float' mode).
 
     tracks : list of [x, y, z, ux, uy, uz, w(, it_start)] (calc.py:110-116)
     weights: per-track weights after normalisation

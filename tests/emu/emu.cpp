@@ -59,7 +59,7 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   bool ok = false;
 #define EMU_CASE(K, M, TWV)                                                                     \
   if (kind == K && g->mode == M && tw == TWV) {                                                 \
-    if (f32) run_all<Cfg<float, float, M, K, TWV, false>>(P, counters);                         \
+    if (f32) run_all<Cfg<double, float, M, K, TWV, false>>(P, counters);                         \
     else run_all<Cfg<double, double, M, K, TWV, false>>(P, counters);                           \
     ok = true; }
   EMU_CASE(KIND_RECUR, MODE_FAR, 16) EMU_CASE(KIND_RECUR, MODE_FAR, 8) EMU_CASE(KIND_RECUR, MODE_FAR, 4)

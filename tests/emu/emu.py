@@ -33,9 +33,9 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     if A['mode'] == 'near':
         A['L_screen'] = L_screen
     A['timeStep'] = dtype(timeStep)
-    T = host.grid_tables(A, dtype)
+    T = host.grid_tables(A)
     weights = [t[6] for t in tracks]
-    pk = host.pack_tracks(tracks, weights, dtype, it_range, nSnaps)
+    pk = host.pack_tracks(tracks, weights, np.double, it_range, nSnaps)
     n_w, n_2, n_p = (int(v) for v in A['gridNodeNums'])
     g = _lib.srb_grid()
     g.mode, g.comp = _lib.MODE[A['mode']], _lib.COMP[comp]
@@ -48,10 +48,10 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
         g.sinTheta, g.cosTheta = T['sinTheta'].ctypes.data, T['cosTheta'].ctypes.data
     else:
         g.radius = T['radius'].ctypes.data
-        g.L_screen = float(dtype(L_screen))
-    ff = host.form_factor(A, dtype)
+        g.L_screen = float(L_screen)
+    ff = host.form_factor(A)
     g.formFactor = ff.ctypes.data
-    g.dt = float(dtype(timeStep))
+    g.dt = float(timeStep)
     g.omega_first_host, g.omega_last_host = float(T['omega'][0]), float(T['omega'][-1])
     t = _lib.srb_tracks()
     t.nTracks = pk.n

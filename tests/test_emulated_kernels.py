@@ -1,0 +1,110 @@
+"""Kernel LOGIC against the oracle on the CPU: the device code of srb_core.cuh compiled by g++ and
+run one warp at a time (tests/emu, test infrastructure only).  Covers what can go wrong
+independently of the hardware: flush chains, Nyquist ranges, phasor seeds and recurrences, tile /
+chunk indexing, particle-chunk partial spectra.  The GPU parity tests (-m gpu) are the real gate."""
+import numpy as np
+import pytest
+
+import cases
+from conftest import rel_errors
+from emu import emu
+
+
+def check(oracle, args, tracks, dt, kinds=('direct', 'recur'), tol=1e-9, nPC=1, tw=None, **kw):
+    ref = oracle.calculate_spectrum(args, tracks, dt, **kw)
+    for kind in kinds:
+        rad, cnt = emu.run(args, tracks, dt, kind=kind, nPC=nPC, tw=tw if kind == 'recur' else None, **kw)
+        for key, r in ref['radiation'].items():
+            e = rel_errors(rad[key], r)
+            limit = 1e-13 if kind == 'direct' else tol
+            assert max(e) < limit, (kind, key, e)
+    return ref, cnt
+
+
+@pytest.mark.parametrize('comp', ['total', 'cartesian', 'cartesian_complex', 'spheric', 'spheric_complex'])
+def test_far_components(oracle, comp):
+    tr, dt, info = cases.undulator_tracks(2, seed=1)
+    check(oracle, cases.undulator_args(info, grid=(100, 4, 3)), tr, dt, comp=comp, sigma_particle=2e-5)
+
+
+@pytest.mark.parametrize('comp', ['total', 'cartesian', 'cartesian_complex'])
+def test_near_components(oracle, comp):
+    tr, dt, info = cases.undulator_tracks(2, near=True, seed=2)
+    check(oracle, cases.undulator_args(info, near=True, grid=(40, 5, 3)), tr, dt, comp=comp,
+          L_screen=1e5, nPC=2)
+
+
+def test_near_small_screen_distance_uses_recurrence(oracle):
+    tr, dt, info = cases.undulator_tracks(1, near=True)
+    args = cases.undulator_args(info, near=True, grid=(64, 4, 2), L_scr=2.0)
+    args['grid'][0] = (1.0, 40.0)
+    check(oracle, args, tr, dt, L_screen=2.0, tol=1e-10)
+
+
+def test_snapshots_and_particle_chunks(oracle):
+    tr, dt, info = cases.undulator_tracks(3, seed=1)
+    _, cnt = check(oracle, cases.undulator_args(info, grid=(70, 5, 3)), tr, dt, nSnaps=4, nPC=2)
+    assert cnt[1] == 3 * 1664 * 70 * 5 * 3
+
+
+def test_global_it_range_with_it_start(oracle):
+    tr, dt, info = cases.undulator_tracks(3, seed=1)
+    tr2 = [t[:7] + [s] for t, s in zip(tr, [0, 5, 17])]
+    check(oracle, cases.undulator_args(info, grid=(70, 5, 3)), tr2, dt, nSnaps=3, it_range=(0, 1500), nPC=3)
+    check(oracle, cases.undulator_args(info, grid=(70, 5, 3)), tr2, dt, nSnaps=5, it_range=(3, 2000))
+
+
+def test_flush_chain_quirks(oracle):
+    """Q3: a track whose it_start sits exactly one below a snapshot never flushes; duplicate
+    snapshot iterations stall the chain; it_range shorter than the track truncates it."""
+    tr, dt, info = cases.undulator_tracks(3, seed=4)
+    args = cases.undulator_args(info, grid=(33, 3, 2))
+    short = [[c[:40] for c in t[:6]] + [t[6]] for t in tr]
+    snaps = np.linspace(0, 30, 4, dtype=np.uint32)[1:]             # [10, 20, 30]
+    tr3 = [short[0] + [int(snaps[0]) - 1], short[1] + [2], short[2] + [int(snaps[1]) - 2]]
+    check(oracle, args, tr3, dt, nSnaps=3, it_range=(0, 30))
+    check(oracle, args, short, dt, nSnaps=50)                       # more snapshots than steps -> duplicates
+    check(oracle, args, short, dt, nSnaps=2, it_range=(0, 25))
+
+
+@pytest.mark.parametrize('grid,tw', [((256, 3, 2), 16), ((300, 3, 2), 16), ((128, 3, 2), 8), ((36, 3, 2), 4),
+                                     ((1, 3, 2), None), ((2, 2, 1), None)])
+def test_omega_chunking_and_tile_widths(oracle, grid, tw):
+    tr, dt = cases.c5_tracks_numpy(2, 300)
+    kinds = ('direct',) if grid[0] < 2 else ('direct', 'recur')
+    check(oracle, cases.c5_args(grid=grid), tr, dt, kinds=kinds, tw=tw)
+
+
+def test_guard_dominated_wiggler(oracle):
+    tr, dt, info = cases.wiggler_tracks(4, 200)
+    ref, cnt = check(oracle, cases.wiggler_args(info, grid=(256, 4, 3)), tr, dt, comp='cartesian', nPC=2)
+    assert cnt[0] == ref['passed'] and cnt[0] < 0.05 * cnt[1]       # identical per-node guard decisions
+
+
+def test_si_units_large_phase_falls_back_per_step(oracle):
+    tr, dt, info = cases.wiggler_tracks(3, 200, si_scale=1e-3)
+    check(oracle, cases.wiggler_args(info, grid=(200, 4, 3), si_scale=1e-3), tr, dt, tol=1e-12)
+
+
+@pytest.mark.parametrize('feature', ['wavelengthGrid', 'logGrid'])
+def test_nonuniform_grids_direct(oracle, feature):
+    tr, dt, info = cases.wiggler_tracks(3, 200)
+    ref, cnt = check(oracle, cases.wiggler_args(info, grid=(150, 4, 3), features=[feature]), tr, dt,
+                     kinds=('direct',))
+    assert cnt[0] == ref['passed']
+
+
+def test_float_mixed_precision_is_no_worse_than_literal_fp32(oracle):
+    """fp32 protocol: the kernel keeps tau / seeds in fp64 and only the per-omega work
+    in fp32, so it must sit closer to the fp64 answer than the literal fp32 restatement does."""
+    tr, dt, info = cases.undulator_tracks(1)
+    a64 = cases.undulator_args(info, grid=(128, 6, 2))
+    a32 = cases.undulator_args(info, grid=(128, 6, 2), dtype='float')
+    r64 = oracle.calculate_spectrum(a64, tr, dt)['radiation']['total']
+    lit = oracle.calculate_spectrum(a32, tr, dt)['radiation']['total']
+    e_lit = rel_errors(lit, r64)
+    for kind in ('direct', 'recur'):
+        rad, _ = emu.run(a32, tr, dt, kind=kind)
+        e = rel_errors(rad['total'], r64)
+        assert e[0] <= e_lit[0] and e[1] <= e_lit[1], (kind, e, e_lit)
+        assert max(e) < 2e-4, (kind, e)

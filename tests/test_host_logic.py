@@ -1,0 +1,107 @@
+"""Host-side semantics of calc_input and track packing (calc.py:355-451, 579-630)."""
+import numpy as np
+import pytest
+
+from synchrad_b200 import host
+
+
+def test_grid_axes_far_defaults():
+    A, dt = host.init_args({'grid': [(1.0, 3.0), (0.0, 0.2), (0.0, 2 * np.pi), (5, 3, 4)]})
+    assert dt is np.double and A['mode'] == 'far' and A['dtype'] == 'double' and A['ctx'] is None
+    np.testing.assert_allclose(A['omega'], [1, 1.5, 2, 2.5, 3])
+    np.testing.assert_allclose(A['theta'], [0, 0.1, 0.2])
+    np.testing.assert_allclose(A['phi'], 2 * np.pi / 4 * np.arange(4))     # end point excluded
+    np.testing.assert_allclose(A['dw'], 0.5)
+    assert A['numGridNodes'] == 60 and tuple(A['gridNodeNums']) == (5, 3, 4)
+    np.testing.assert_allclose(A['dV'], 0.5 * 0.1 * (np.pi / 2))
+    assert host.omega_is_uniform(A)
+
+
+def test_grid_features_and_near():
+    A, _ = host.init_args({'grid': [(1.0, 4.0), (0.0, 2.0), (0.0, 1.0), (4, 3, 1)], 'mode': 'near',
+                           'Features': ['wavelengthGrid']})
+    np.testing.assert_allclose(A['omega'], 1 / np.linspace(0.25, 1, 4))      # descending omega
+    assert A['dph'] == 1.0 and 'radius' in A and 'theta' not in A and A['dr'] == 1.0
+    assert not host.omega_is_uniform(A)
+    B, _ = host.init_args({'grid': [(1.0, 8.0), (0.0, 2.0), (0.0, 1.0), (4, 3, 2)], 'Features': ['logGrid']})
+    np.testing.assert_allclose(B['omega'], [1, 2, 4, 8])
+    assert not host.omega_is_uniform(B)
+
+
+def test_float_dtype_and_alias(capsys):
+    A, dt = host.init_args({'grid': [(1.0, 3.0), (0.0, 0.2), (0.0, 1.0), (5, 3, 4)], 'dtype': 'float'})
+    assert dt is np.single and A['omega'].dtype == np.float32 and A['dw'].dtype == np.float64
+    assert 'WARNING' in capsys.readouterr().out
+    _, dt2 = host.init_args({'grid': [(1.0, 3.0), (0.0, 0.2), (0.0, 1.0), (5, 3, 4)], 'dtype': 'single'})
+    assert dt2 is np.single
+    with pytest.raises(ValueError):
+        host.init_args({'grid': [(1.0, 3.0), (0.0, 0.2), (0.0, 1.0), (5, 3, 4)], 'dtype': 'half'})
+
+
+def test_tables_are_two_pi_omega():
+    A, dt = host.init_args({'grid': [(1.0, 3.0), (0.0, 0.2), (0.0, 1.0), (5, 3, 4)]})
+    T = host.grid_tables(A)
+    assert all(v.dtype == np.float64 for v in T.values())
+    np.testing.assert_array_equal(T['omega'], np.double(2 * np.pi) * A['omega'])    # calc.py:494-495
+    np.testing.assert_array_equal(T['sinTheta'], np.sin(A['theta']))
+    # 'float': user-visible axes are float32 like the reference's, device tables stay float64
+    # and are built from the un-rounded axes (mixed precision, see host.grid_tables)
+    F, _ = host.init_args({'grid': [(1.0, 3.0), (0.0, 0.2), (0.0, 1.0), (5, 3, 4)], 'dtype': 'float'})
+    assert F['omega'].dtype == np.float32
+    np.testing.assert_array_equal(host.grid_tables(F)['omega'], T['omega'])
+
+
+def test_snap_iterations():
+    np.testing.assert_array_equal(host.snap_iterations((0, 10), 1), [10])
+    np.testing.assert_array_equal(host.snap_iterations((0, 10), 4), [2, 5, 7, 10])   # floor of 2.5, 7.5
+    assert host.snap_iterations((3, 11), 2).dtype == np.uint32
+
+
+def test_select_tracks_round_robin():
+    np.testing.assert_array_equal(host.select_tracks(10, None, 1, 4), [1, 5, 9])
+    np.testing.assert_array_equal(host.select_tracks(10, 6, 0, 4), [0, 4])
+    np.testing.assert_array_equal(host.select_tracks(3, 100, 3, 4), [])
+
+
+def test_weights_normalize_is_rank_local():
+    np.testing.assert_allclose(host.normalized_weights([1, 3], 'mean'), [0.5, 1.5])
+    np.testing.assert_allclose(host.normalized_weights([1, 4], 'max'), [0.25, 1.0])
+    np.testing.assert_allclose(host.normalized_weights([1, 4], 'ones'), [1, 1])
+    np.testing.assert_allclose(host.normalized_weights([1, 4], None), [1, 4])
+
+
+def _tracks():
+    rs = np.random.RandomState(0)
+    return [[rs.rand(n) for _ in range(6)] + [w, s] for n, w, s in ((5, 1.0, 0), (9, 2.5, 3), (1, 0.5, 7))]
+
+
+def test_pack_tracks_per_track_ranges():
+    tr = _tracks()
+    P = host.pack_tracks(tr, [t[6] for t in tr], np.float32, None, 2)
+    np.testing.assert_array_equal(P.offsets, [0, 5, 14, 15])
+    assert P.coords[0].dtype == np.float32 and P.total == 15
+    np.testing.assert_array_equal(P.coords[3][5:14], tr[1][3].astype(np.float32))
+    np.testing.assert_array_equal(P.itStart[:3], [0, 0, 0])            # it_start forced to 0 (calc.py:299)
+    np.testing.assert_array_equal(P.itEnd[:3], [5, 9, 1])
+    assert P.snapStride == 2
+    np.testing.assert_array_equal(P.itSnaps[1], host.snap_iterations((0, 9), 2))
+    assert P.updates_per_node == 4 + 8 + 0
+
+
+def test_pack_tracks_global_range_and_seven_element_tracks():
+    tr = _tracks()
+    tr[0] = tr[0][:7]                                                    # it_start defaults to 0
+    P = host.pack_tracks(tr, [1, 1, 1], np.float64, (2, 8), 3)
+    np.testing.assert_array_equal(P.itStart[:3], [0, 3, 7])
+    np.testing.assert_array_equal(P.itEnd[:3], [8, 8, 8])
+    assert P.snapStride == 0 and P.itSnaps.shape == (3,)
+    assert P.updates_per_node == 4 + 7 + 0
+
+
+def test_pack_tracks_empty_and_ragged():
+    P = host.pack_tracks([], [], np.float64, None, 1)
+    assert P.n == 0 and P.total == 0
+    bad = _tracks()
+    bad[0][2] = np.zeros(3)
+    with pytest.raises(ValueError):
+        host.pack_tracks(bad, [1, 1, 1], np.float64, None, 1)
