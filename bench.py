@@ -259,7 +259,10 @@ def run_product(a):
     k_ms = sum(kernel_ms) / len(kernel_ms)
     slots_alg = ALG_SLOTS[a.dtype]
     achieved = updates_rank * slots_alg / (k_ms * 1e-3)          # algorithmic slots/s of one launch
-    issued = {1: {16: 62.0 / 16 * 2, 8: 30.0 / 8 * 2, 4: 14.0 / 4 * 2}}.get(int(info.kind), {}).get(int(info.tile_width))
+    issued = None
+    if int(info.kind) == 1:      # recurrence: per lane and step (TW-2) chain + NC*TW accumulate + 2 seed ops, for TW half-updates
+        tw, nc = int(info.tile_width), int(info.n_components)
+        issued = 2.0 * ((tw - 2) + nc * tw + 2) / tw
     roofline = {
         'bound': 'fp64_pipe' if a.dtype == 'double' else 'fp32_pipe',
         'achieved': achieved / 1e12, 'peak': peak.value / 1e12, 'unit': 'Tslot/s (FMA-pipe lane issue slots)',

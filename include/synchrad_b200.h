@@ -138,6 +138,7 @@ typedef struct srb_launch_info {
   uint32_t chunk_nodes, n_chunks, n_virtual_dirs, n_particle_chunks;
   uint32_t grid_blocks, block_threads, smem_bytes;
   uint32_t kernels_launched;
+  uint32_t n_components;  /* far-field amplitude components carried per node (2 transverse | 3) */
 } srb_launch_info;
 int srb_last_launch(srb_launch_info* info);
 

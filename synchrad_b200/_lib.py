@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libsynchrad_b200.so')
+LIB_PATH = os.environ.get('SYNCHRAD_B200_LIB') or os.path.join(_HERE, 'csrc', 'libsynchrad_b200.so')
 
 MODE = {'far': 0, 'near': 1}
 COMP = {'total': 0, 'cartesian': 1, 'cartesian_complex': 2, 'spheric': 3, 'spheric_complex': 4}
@@ -54,6 +54,7 @@ class srb_launch_info(ctypes.Structure):
         ('n_virtual_dirs', ctypes.c_uint32), ('n_particle_chunks', ctypes.c_uint32),
         ('grid_blocks', ctypes.c_uint32), ('block_threads', ctypes.c_uint32),
         ('smem_bytes', ctypes.c_uint32), ('kernels_launched', ctypes.c_uint32),
+        ('n_components', ctypes.c_uint32),
     ]
 
 

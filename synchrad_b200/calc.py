@@ -209,21 +209,10 @@ class SynchRad(Utilities):
         dev_out = engine.to_host_layout(res.spectra, nSnaps, n_w, n_2, n_p)
         keys = host.COMP_KEYS[comp]
 
+        cnt = res.counters
         if self.size > 1:                       # replaces _gather_result_mpi (calc.py:560-571)
-            buf = torch.stack(dev_out)
-            self.comm.reduce(buf, dst=0, op=self.comm.ReduceOp.SUM)
-            tw = torch.tensor([self.total_weight], dtype=torch.float64, device=buf.device)
-            self.comm.reduce(tw, dst=0, op=self.comm.ReduceOp.SUM)
-            cnt = res.counters.clone()
-            self.comm.reduce(cnt, dst=0, op=self.comm.ReduceOp.SUM)
-            if self.rank == 0:
-                dev_out = list(buf.unbind(0))
-                self.total_weight = float(tw.item())
-            else:                               # non-root ranks end with zeros / None (a16)
-                dev_out = [torch.zeros_like(b) for b in buf.unbind(0)]
-                self.total_weight = None
-        else:
-            cnt = res.counters
+            from .dist import reduce_to_root
+            dev_out, self.total_weight, cnt = reduce_to_root(self.comm, dev_out, self.total_weight, cnt)
         self.Data['radiation'] = {k: d.cpu().numpy() for k, d in zip(keys, dev_out)}
         c = cnt.cpu().numpy()
         self.last_run = {

@@ -25,10 +25,28 @@ int fail(const std::string& m) { g_err = m; return -1; }
       return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
   } while (0)
 
-constexpr int NW = 8;   // warps (= virtual directions) per block
+// Block shape (measured on B200, profiles/r01_tuning.md): 4 warps (= 4 virtual directions) per
+// block; the recurrence kernels run 4 blocks/SM (16 warps, <=128 registers), the direct kernels
+// (48 accumulators + sincos temporaries) 2 blocks/SM.
+#ifndef SRB_NW
+#define SRB_NW 4
+#endif
+#ifndef SRB_MINB
+#define SRB_MINB 4
+#endif
+#ifndef SRB_MINB_DIRECT
+#define SRB_MINB_DIRECT 2
+#endif
+constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
+
+// resident blocks per SM the register budget is tuned for: accumulators must stay in registers
+template <class C> constexpr int min_blocks() {
+  constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
+  return C::KIND == srb::KIND_DIRECT ? SRB_MINB_DIRECT : (accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB));
+}
 
 template <class C>
-__global__ void __launch_bounds__(NW * 32, 1) k_integrate(const srb::Params P) {
+__global__ void __launch_bounds__(NW * 32, min_blocks<C>()) k_integrate(const srb::Params P) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const uint32_t warp = threadIdx.x >> 5;
   srb::WarpSmem<C>* sm = reinterpret_cast<srb::WarpSmem<C>*>(smraw) + warp;
@@ -38,6 +56,31 @@ __global__ void __launch_bounds__(NW * 32, 1) k_integrate(const srb::Params P) {
   if (vd >= P.nVD) return;
   srb::ThreadState<C> st;
   srb::warp_task<C>(P, vd, pc, *sm, &st);
+}
+
+// Direction-independent per-step kinematics, once per call (instead of once per direction):
+// far: a = (beta_{it+1}-beta_it)/dt and b = (beta_{it+1}+beta_it)/2 ; near: beta_it.
+// Same strict operation order as the in-kernel path, so results are bit-identical.
+__global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_t total) {
+  const double dtInv = srb::sdiv(1.0, P.dt);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t a = 0, b = P.nTracks;          // last track with offsets[t] <= i
+    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (P.offsets[mid] <= i) a = mid; else b = mid; }
+    const uint64_t o = P.offsets[a];
+    const uint64_t n = P.offsets[a + 1] - o;
+    const uint64_t it = i - o;
+    if (P.mode == srb::MODE_FAR) {
+      double av[3] = {0, 0, 0}, bv[3] = {0, 0, 0};
+      if (it + 1 < n) srb::far_step_kinematics<double>(P.ux, P.uy, P.uz, i, dtInv, av, bv);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { pre[c * total + i] = av[c]; pre[(3 + c) * total + i] = bv[c]; }
+    } else {
+      double bv[3];
+      srb::near_step_kinematics<double>(P.ux, P.uy, P.uz, i, bv);
+#pragma unroll
+      for (int c = 0; c < 3; c++) pre[c * total + i] = bv[c];
+    }
+  }
 }
 
 // out[c][i] += sum over particle chunks of the private partial spectra (fixed order: deterministic)
@@ -95,50 +138,33 @@ template <class C> Launcher make_launcher() {
 
 using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::MODE_FAR; using srb::MODE_NEAR;
 
-// kind, mode, dtype, native, tile width -> kernel
-bool pick(int kind, int mode, int dtype, bool native, int tw, Launcher* L) {
-#define SRB_CASE(K, M, D, NAT, TWV, TI, TM)                                                   \
-  if (kind == K && mode == M && dtype == D && native == NAT && tw == TWV) {                   \
-    *L = make_launcher<Cfg<TI, TM, M, K, TWV, NAT>>(); return true; }
-  // recurrence, far
-  SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 16, double, double)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 8, double, double)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 0, false, 4, double, double)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 16, double, float)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 8, double, float)
-  SRB_CASE(KIND_RECUR, MODE_FAR, 1, false, 4, double, float)
+// kind, mode, dtype, native, tile width, far components -> kernel
+bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* L) {
+#define SRB_CASE(K, M, D, NAT, TWV, NCV, TM)                                                        \
+  if (kind == K && mode == M && dtype == D && native == NAT && tw == TWV && nc == NCV) {            \
+    *L = make_launcher<Cfg<double, TM, M, K, TWV, NAT, NCV>>(); return true; }
+#define SRB_BOTH(K, M, NAT, TWV, NCV) SRB_CASE(K, M, 0, NAT, TWV, NCV, double) SRB_CASE(K, M, 1, NAT, TWV, NCV, float)
+  // recurrence, far: transverse (NC=2) for total/cartesian(_complex), NC=3 for the spheric kernels
+  SRB_BOTH(KIND_RECUR, MODE_FAR, false, 16, 2) SRB_BOTH(KIND_RECUR, MODE_FAR, false, 8, 2) SRB_BOTH(KIND_RECUR, MODE_FAR, false, 4, 2)
+  SRB_BOTH(KIND_RECUR, MODE_FAR, false, 16, 3) SRB_BOTH(KIND_RECUR, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_RECUR, MODE_FAR, false, 4, 3)
   // recurrence, near
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 8, double, double)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 4, double, double)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 0, false, 2, double, double)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 8, double, float)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 4, double, float)
-  SRB_CASE(KIND_RECUR, MODE_NEAR, 1, false, 2, double, float)
+  SRB_BOTH(KIND_RECUR, MODE_NEAR, false, 8, 3) SRB_BOTH(KIND_RECUR, MODE_NEAR, false, 4, 3) SRB_BOTH(KIND_RECUR, MODE_NEAR, false, 2, 3)
   // direct
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 8, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 4, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 0, false, 2, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 8, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 4, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 0, false, 2, double, double)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 8, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 4, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, false, 2, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 8, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 4, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, false, 2, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 8, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 4, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, double, float)
-  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, double, float)
+  SRB_BOTH(KIND_DIRECT, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_DIRECT, MODE_FAR, false, 4, 3) SRB_BOTH(KIND_DIRECT, MODE_FAR, false, 2, 3)
+  SRB_BOTH(KIND_DIRECT, MODE_NEAR, false, 8, 3) SRB_BOTH(KIND_DIRECT, MODE_NEAR, false, 4, 3) SRB_BOTH(KIND_DIRECT, MODE_NEAR, false, 2, 3)
+  // direct, fp32 native sincos
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 8, 3, float) SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 4, 3, float)
+  SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, 3, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, 3, float) SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, 3, float)
+  SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, 3, float)
+#undef SRB_BOTH
 #undef SRB_CASE
   return false;
 }
 
 struct Plan {
-  int kind, tw;
+  int kind, tw, nc;
+  size_t preDoubles;      // doubles of scratch used by the per-step pre-pass (0 = computed in-kernel)
   bool native;
   Launcher L;
   uint32_t chunkNodes, nChunks, nVD, nVDtiles, nPC;
@@ -186,7 +212,9 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   else { twMax = 8; twMin = 2; }
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }
-  if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, &p->L)) return fail("internal: no kernel for this configuration");
+  const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
+  p->nc = (p->kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
+  if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L)) return fail("internal: no kernel for this configuration");
   p->chunkNodes = (uint32_t)p->L.chunk;
   p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;
   p->nVD = g->nPhi * g->nAxis2 * p->nChunks;
@@ -200,6 +228,12 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   // particle chunks: fill whole waves of the machine; bounded by tracks, scratch and 64 waves
   const uint64_t slots = (uint64_t)p->numSM * p->blocksPerSM;
   uint64_t maxPC = t->nTracks ? t->nTracks : 1;
+  // scratch = [pre-pass planes][private partial spectra]; the pre-pass is used when it fits
+  p->preDoubles = (size_t)(g->mode == SRB_MODE_FAR ? 6 : 3) * t->totalSteps_host;
+  if (!unlimited) {
+    if (scratch_bytes >= p->preDoubles * 8) scratch_bytes -= p->preDoubles * 8;
+    else p->preDoubles = 0;
+  }
   const uint64_t slabCap = unlimited ? (uint64_t)(1ull << 30) / (p->slabDoubles * 8) : scratch_bytes / (p->slabDoubles * 8);
   maxPC = std::min<uint64_t>(maxPC, 1 + slabCap);
   maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, (64 * slots) / p->nVDtiles));
@@ -238,7 +272,7 @@ size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks) {
   if (validate(grid, tracks) != 0) return 0;
   Plan p;
   if (make_plan(grid, tracks, 0, true, &p) != 0) return 0;
-  return (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double);
+  return ((size_t)(p.nPC - 1) * p.slabDoubles + p.preDoubles) * sizeof(double);
 }
 
 int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int n_spectra,
@@ -270,11 +304,20 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   P.offsets = t->offsets; P.w = t->w; P.itStart = t->itStart; P.itEnd = t->itEnd; P.itSnaps = t->itSnaps;
   P.snapStride = t->itSnapsStride;
   for (int c = 0; c < p.nOut; c++) P.out[c] = spectra[c];
-  P.slabs = (double*)scratch; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
+  double* preBuf = p.preDoubles ? (double*)scratch : nullptr;
+  P.pre = preBuf; P.preStride = t->totalSteps_host;
+  P.slabs = (double*)scratch + p.preDoubles; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
   P.counters = (unsigned long long*)counters;
 
   uint32_t launched = 0;
-  if (p.nPC > 1) SRB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double), stream));
+  if (preBuf) {
+    const uint64_t total = t->totalSteps_host;
+    const int pb = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)p.numSM * 16);
+    k_prepass<<<pb, 256, 0, stream>>>(P, preBuf, total);
+    SRB_CUDA(cudaGetLastError());
+    launched++;
+  }
+  if (p.nPC > 1) SRB_CUDA(cudaMemsetAsync(P.slabs, 0, (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double), stream));
   const uint32_t blocks = p.nVDtiles * p.nPC;
   p.L.kernel<<<blocks, NW * 32, p.L.smem, stream>>>(P);
   SRB_CUDA(cudaGetLastError());
@@ -288,7 +331,7 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   }
   g_info.kind = p.kind; g_info.tile_width = p.tw; g_info.chunk_nodes = p.chunkNodes; g_info.n_chunks = p.nChunks;
   g_info.n_virtual_dirs = p.nVD; g_info.n_particle_chunks = p.nPC; g_info.grid_blocks = blocks;
-  g_info.block_threads = NW * 32; g_info.smem_bytes = (uint32_t)p.L.smem; g_info.kernels_launched = launched;
+  g_info.block_threads = NW * 32; g_info.n_components = (uint32_t)p.nc; g_info.smem_bytes = (uint32_t)p.L.smem; g_info.kernels_launched = launched;
   return 0;
 }
 

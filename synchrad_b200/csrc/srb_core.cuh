@@ -124,6 +124,21 @@ SRB_HD float tmul(float a, float b) {
   return a * b;
 #endif
 }
+// v with its sign bit XOR-ed by mask (0 or 0x80000000): a lane-dependent sign without an FP64-pipe op
+SRB_HD double flipsign(double v, uint32_t mask) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+#else
+  return mask ? -v : v;
+#endif
+}
+SRB_HD float flipsign(float v, uint32_t mask) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(__float_as_int(v) ^ (int)mask);
+#else
+  return mask ? -v : v;
+#endif
+}
 SRB_HD void sincos_t(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
   sincosf(x, s, c);
@@ -169,26 +184,42 @@ struct Params {
   size_t slabStride;        // doubles per slab = nOut*nSnaps*nTotal
   uint32_t nPC;             // particle chunks
   unsigned long long* counters;  // [0] passed updates, [1] all updates (may be null)
+  // optional per-step pre-pass (direction independent, computed once per call by k_prepass):
+  // SoA planes of `preStride` doubles; far: a0,a1,a2,b0,b1,b2 (acceleration, mean beta),
+  // near: beta0,beta1,beta2.  nullptr -> the prep phase computes them itself.
+  const double* pre;
+  uint64_t preStride;
 };
 
-template <class TI_, class TM_, int MODE_, int KIND_, int TW_, bool NATIVE_>
+// NC: amplitude components carried per node in far-field mode.
+//   3 — Cartesian (or, for the spheric kernels, the (n, e_theta, e_phi) projections);
+//   2 — transverse basis (e_theta, e_phi): the Lienard-Wiechert vector A = c1 (n - beta) - c2 a is
+//       orthogonal to n identically (A.n = c1/c2 - c2 (a.n) = 0; in floating point the residue is
+//       ~1 ulp of |A|), so two components carry everything and the Cartesian ones are rebuilt at
+//       flush time as F = F_theta e_theta + F_phi e_phi.  Used for total / cartesian(_complex).
+template <class TI_, class TM_, int MODE_, int KIND_, int TW_, bool NATIVE_, int NC_ = 3>
 struct Cfg {
   using TI = TI_;   // dtype of tables / tracks
   using TM = TM_;   // arithmetic type of the main phase
-  static constexpr int MODE = MODE_, KIND = KIND_, TW = TW_;
+  static constexpr int MODE = MODE_, KIND = KIND_, TW = TW_, NC = NC_;
   static constexpr bool NATIVE = NATIVE_;
   static constexpr int TILES = (KIND_ == KIND_RECUR) ? 16 : 32;   // omega tiles per chunk
   static constexpr int CHUNK = TILES * TW_;
-  static constexpr int NACC = (KIND_ == KIND_RECUR && MODE_ == MODE_FAR) ? 3 * TW_ : 6 * TW_;
-  static constexpr int NREC = (MODE_ == MODE_FAR) ? 4 : 8;
-  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 64 : 1;
+  static constexpr int NV = (MODE_ == MODE_FAR) ? NC_ : 6;        // per-step vector entries in `rec`
+  // accumulators per node: split layout (recurrence) holds one part (cos or sin) of NV sums,
+  // the direct layout holds Re and Im of the 3 (far: NC) amplitude components
+  static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV : ((MODE_ == MODE_FAR) ? 2 * NC_ : 6);
+  static constexpr int NACC = NPN * TW_;
+  // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
+  static constexpr int NREC = ((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1;
+  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : 1;
 };
 
 template <class C>
 struct WarpSmem {
-  typename C::TM rec[SUB][C::NREC];       // far: A[3], coef|tau ; near: B[3], C[3], coef|tau
+  typename C::TM rec[SUB][C::NREC];       // per-step record (see Cfg::NREC)
   uint32_t rng[SUB];                      // lo | hi<<10 | flag<<30 (chunk-relative pass range)
-  typename C::TM seeds[C::NSEED][SUB + 1];  // [(sel*2+part)*16+tile][step], padded
+  typename C::TM seeds[C::NSEED][SUB + 1];  // [part*16+tile][step]: cos|sin of the tile's first node
 };
 
 template <class C>
@@ -206,10 +237,33 @@ struct Geom {            // one virtual direction
 
 struct TrackView {
   const void *x, *y, *z, *ux, *uy, *uz;   // already offset to the track start
+  const double* pre;                      // pre-pass planes offset to the track start, or null
   uint32_t n, itStart, itEnd;
   const uint32_t* snaps;
   double w;
 };
+
+// direction-independent part of a far-field step: beta_it, beta_it+1 -> acceleration a and
+// mean beta b (kernel_farfield.cl:74-83), strict operation order
+template <class TI>
+SRB_HD void far_step_kinematics(const void* ux, const void* uy, const void* uz, size_t it, double dtInv,
+                                double a[3], double b[3]) {
+  double u0 = (double)((const TI*)ux)[it], u1 = (double)((const TI*)uy)[it], u2 = (double)((const TI*)uz)[it];
+  double v0 = (double)((const TI*)ux)[it + 1], v1 = (double)((const TI*)uy)[it + 1], v2 = (double)((const TI*)uz)[it + 1];
+  double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
+  u0 = smul(u0, gi); u1 = smul(u1, gi); u2 = smul(u2, gi);
+  gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(v0, v1, v2, v0, v1, v2))));
+  v0 = smul(v0, gi); v1 = smul(v1, gi); v2 = smul(v2, gi);
+  a[0] = smul(ssub(v0, u0), dtInv); a[1] = smul(ssub(v1, u1), dtInv); a[2] = smul(ssub(v2, u2), dtInv);
+  b[0] = smul(0.5, sadd(v0, u0)); b[1] = smul(0.5, sadd(v1, u1)); b[2] = smul(0.5, sadd(v2, u2));
+}
+// near field: beta of the single sample (kernel_nearfield.cl:78-81)
+template <class TI>
+SRB_HD void near_step_kinematics(const void* ux, const void* uy, const void* uz, size_t it, double b[3]) {
+  const double u0 = (double)((const TI*)ux)[it], u1 = (double)((const TI*)uy)[it], u2 = (double)((const TI*)uz)[it];
+  const double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
+  b[0] = smul(u0, gi); b[1] = smul(u1, gi); b[2] = smul(u2, gi);
+}
 
 template <class TI> SRB_HD double ldv(const void* p, size_t i) { return (double)((const TI*)p)[i]; }
 
@@ -219,36 +273,39 @@ template <class TI> SRB_HD double ldv(const void* p, size_t i) { return (double)
 // strict restatement of kernel_farfield.cl:65-94 / kernel_nearfield.cl:64-85.
 template <class C>
 SRB_HD void prep_far(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
-                     double dtInv, double& tau, double& tauPrev, double A[3]) {
+                     double dtInv, double& tau, double A[3]) {
   using TI = typename C::TI;
   const double time = smul((double)(tv.itStart + it), P.dt);
   tau = ssub(time, sdot3(ldv<TI>(tv.x, it), ldv<TI>(tv.y, it), ldv<TI>(tv.z, it), g.nx, g.ny, g.nz));
-  if (it == 0) tauPrev = 0.0;   // phasePrev starts at 0 (Q1)
-  else {
-    const double tp = smul((double)(tv.itStart + it - 1), P.dt);
-    tauPrev = ssub(tp, sdot3(ldv<TI>(tv.x, it - 1), ldv<TI>(tv.y, it - 1), ldv<TI>(tv.z, it - 1),
-                             g.nx, g.ny, g.nz));
-  }
-  double u0 = ldv<TI>(tv.ux, it), u1 = ldv<TI>(tv.uy, it), u2 = ldv<TI>(tv.uz, it);
-  double v0 = ldv<TI>(tv.ux, it + 1), v1 = ldv<TI>(tv.uy, it + 1), v2 = ldv<TI>(tv.uz, it + 1);
-  double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
-  u0 = smul(u0, gi); u1 = smul(u1, gi); u2 = smul(u2, gi);
-  gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(v0, v1, v2, v0, v1, v2))));
-  v0 = smul(v0, gi); v1 = smul(v1, gi); v2 = smul(v2, gi);
-  const double a0 = smul(ssub(v0, u0), dtInv), a1 = smul(ssub(v1, u1), dtInv), a2 = smul(ssub(v2, u2), dtInv);
-  const double b0 = smul(0.5, sadd(v0, u0)), b1 = smul(0.5, sadd(v1, u1)), b2 = smul(0.5, sadd(v2, u2));
-  double c1 = sdot3(a0, a1, a2, g.nx, g.ny, g.nz);
-  double c2 = ssub(1.0, sdot3(b0, b1, b2, g.nx, g.ny, g.nz));
+  double a[3], b[3];
+  if (tv.pre) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { a[c] = tv.pre[c * P.preStride + it]; b[c] = tv.pre[(3 + c) * P.preStride + it]; }
+  } else far_step_kinematics<TI>(tv.ux, tv.uy, tv.uz, it, dtInv, a, b);
+  double c1 = sdot3(a[0], a[1], a[2], g.nx, g.ny, g.nz);
+  double c2 = ssub(1.0, sdot3(b[0], b[1], b[2], g.nx, g.ny, g.nz));
   c2 = sdiv(1.0, c2);
   c1 = smul(smul(c1, c2), c2);
-  const double A0 = ssub(smul(c1, ssub(g.nx, b0)), smul(c2, a0));
-  const double A1 = ssub(smul(c1, ssub(g.ny, b1)), smul(c2, a1));
-  const double A2 = ssub(smul(c1, ssub(g.nz, b2)), smul(c2, a2));
-  if (P.comp == COMP_SPH || P.comp == COMP_SPH_CPLX) {   // kernel_farfield.cl:442-445
+  const double A0 = ssub(smul(c1, ssub(g.nx, b[0])), smul(c2, a[0]));
+  const double A1 = ssub(smul(c1, ssub(g.ny, b[1])), smul(c2, a[1]));
+  const double A2 = ssub(smul(c1, ssub(g.nz, b[2])), smul(c2, a[2]));
+  if (C::NC == 2) {              // transverse basis (see Cfg)
+    A[0] = sdot3(g.tx, g.ty, g.tz, A0, A1, A2);
+    A[1] = sdot3(g.px, g.py, g.pz, A0, A1, A2);
+    A[2] = 0.0;
+  } else if (P.comp == COMP_SPH || P.comp == COMP_SPH_CPLX) {   // kernel_farfield.cl:442-445
     A[0] = sdot3(g.nx, g.ny, g.nz, A0, A1, A2);
     A[1] = sdot3(g.tx, g.ty, g.tz, A0, A1, A2);
     A[2] = sdot3(g.px, g.py, g.pz, A0, A1, A2);
   } else { A[0] = A0; A[1] = A1; A[2] = A2; }
+}
+
+// tau of step it-1 (the reference's phasePrev/omega), or 0 for it == 0 (Q1)
+template <class C>
+SRB_HD double far_tau(const Params& P, const Geom& g, const TrackView& tv, uint32_t it) {
+  using TI = typename C::TI;
+  const double tp = smul((double)(tv.itStart + it), P.dt);
+  return ssub(tp, sdot3(ldv<TI>(tv.x, it), ldv<TI>(tv.y, it), ldv<TI>(tv.z, it), g.nx, g.ny, g.nz));
 }
 
 template <class C>
@@ -264,18 +321,18 @@ SRB_HD void near_tau(const Params& P, const Geom& g, const TrackView& tv, uint32
 // near: B = rInv*(beta - n), Cv = rInv^2 * n ; the reference's c1 = omega*B, c2 = Cv
 template <class C>
 SRB_HD void prep_near(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
-                      double& tau, double& tauPrev, double B[3], double Cv[3]) {
+                      double& tau, double B[3], double Cv[3]) {
   using TI = typename C::TI;
   double r0, r1, r2, rL;
   near_tau<C>(P, g, tv, it, tau, r0, r1, r2, rL);
-  if (it == 0) tauPrev = 0.0;
-  else { double q0, q1, q2, qL; near_tau<C>(P, g, tv, it - 1, tauPrev, q0, q1, q2, qL); }
   const double rInv = sdiv(1.0, rL);
   const double n0 = smul(rInv, r0), n1 = smul(rInv, r1), n2 = smul(rInv, r2);
-  double u0 = ldv<TI>(tv.ux, it), u1 = ldv<TI>(tv.uy, it), u2 = ldv<TI>(tv.uz, it);
-  const double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
-  u0 = smul(u0, gi); u1 = smul(u1, gi); u2 = smul(u2, gi);
-  B[0] = smul(rInv, ssub(u0, n0)); B[1] = smul(rInv, ssub(u1, n1)); B[2] = smul(rInv, ssub(u2, n2));
+  double u[3];
+  if (tv.pre) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) u[c] = tv.pre[c * P.preStride + it];
+  } else near_step_kinematics<TI>(tv.ux, tv.uy, tv.uz, it, u);
+  B[0] = smul(rInv, ssub(u[0], n0)); B[1] = smul(rInv, ssub(u[1], n1)); B[2] = smul(rInv, ssub(u[2], n2));
   const double ri2 = smul(rInv, rInv);
   Cv[0] = smul(ri2, n0); Cv[1] = smul(ri2, n1); Cv[2] = smul(ri2, n2);
 }
@@ -309,48 +366,56 @@ SRB_HD void pass_range(const Params& P, const Geom& g, double tau, double tauPre
 }
 
 // Phasor seeds for the 16 omega tiles of a chunk (uniform grid): X_m = exp(i(phi0 + m*TW*d)),
-// Y_m = X_m * exp(i*d), generated with the three-term recurrence in m.  phi0 is the reference's
-// own rounded phase at the chunk's first node.
+// generated with the three-term recurrence in m.  phi0 is the reference's own rounded phase at
+// the chunk's first node.  The main phase derives the tile's second node as X_m * exp(i*d).
 template <class C>
-SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& sm, int s, double& coef) {
+SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& sm, int s, double out[3]) {
   using TI = typename C::TI; using TM = typename C::TM;
   const double w0 = (double)((const TI*)P.omega)[g.cLo];
   double s0, c0, sd, cd;
   sincos_big(smul(w0, tau), &s0, &c0);
   sincos_big(P.domega * tau, &sd, &cd);
-  coef = 2.0 * cd;
+  out[0] = 2.0 * cd; out[1] = cd; out[2] = sd;
   double cw = cd, sw = sd;
 #pragma unroll
   for (int i = 1; i < C::TW; i <<= 1) { const double t = cw * cw - sw * sw; sw = 2.0 * cw * sw; cw = t; }
   double xr0 = c0, xi0 = s0;
   double xr1 = c0 * cw - s0 * sw, xi1 = c0 * sw + s0 * cw;
-  double yr0 = c0 * cd - s0 * sd, yi0 = c0 * sd + s0 * cd;
-  double yr1 = xr1 * cd - xi1 * sd, yi1 = xr1 * sd + xi1 * cd;
   const double cf = 2.0 * cw;
-  sm.seeds[0][s] = (TM)xr0;  sm.seeds[16][s] = (TM)xi0;  sm.seeds[32][s] = (TM)yr0;  sm.seeds[48][s] = (TM)yi0;
-  sm.seeds[1][s] = (TM)xr1;  sm.seeds[17][s] = (TM)xi1;  sm.seeds[33][s] = (TM)yr1;  sm.seeds[49][s] = (TM)yi1;
+  sm.seeds[0][s] = (TM)xr0;  sm.seeds[16][s] = (TM)xi0;
+  sm.seeds[1][s] = (TM)xr1;  sm.seeds[17][s] = (TM)xi1;
 #pragma unroll
   for (int m = 2; m < 16; m++) {
-    const double xr2 = cf * xr1 - xr0, xi2 = cf * xi1 - xi0, yr2 = cf * yr1 - yr0, yi2 = cf * yi1 - yi0;
-    sm.seeds[m][s] = (TM)xr2; sm.seeds[16 + m][s] = (TM)xi2; sm.seeds[32 + m][s] = (TM)yr2; sm.seeds[48 + m][s] = (TM)yi2;
-    xr0 = xr1; xi0 = xi1; yr0 = yr1; yi0 = yi1; xr1 = xr2; xi1 = xi2; yr1 = yr2; yi1 = yi2;
+    const double xr2 = cf * xr1 - xr0, xi2 = cf * xi1 - xi0;
+    sm.seeds[m][s] = (TM)xr2; sm.seeds[16 + m][s] = (TM)xi2;
+    xr0 = xr1; xi0 = xi1; xr1 = xr2; xi1 = xi2;
   }
 }
 
 template <class C>
-SRB_HD void prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint32_t itBase, int cnt,
-                       double dtInv, int lane, WarpSmem<C>& sm, ThreadState<C>& st) {
+SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint32_t itBase, int cnt,
+                           double dtInv, int lane, WarpSmem<C>& sm, ThreadState<C>& st) {
   using TM = typename C::TM;
-  if (lane >= cnt) return;
+  if (lane >= cnt) return 0u;
   const uint32_t it = itBase + (uint32_t)lane;
   double tau, tauPrev, V[6];
-  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, tau, tauPrev, V);
-  else prep_near<C>(P, g, tv, it, tau, tauPrev, V, V + 3);
+  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, tau, V);
+  else prep_near<C>(P, g, tv, it, tau, V, V + 3);
+  // tau of the previous step: the neighbouring lane has it (lanes [0,cnt) are all here)
+#if defined(__CUDA_ARCH__)
+  tauPrev = __shfl_up_sync(cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u), tau, 1);
+  if (lane == 0)
+#endif
+  {
+    if (it == 0) tauPrev = 0.0;        // phasePrev starts at 0 (Q1)
+    else if (C::MODE == MODE_FAR) tauPrev = far_tau<C>(P, g, tv, it - 1);
+    else { double q0, q1, q2, qL; near_tau<C>(P, g, tv, it - 1, tauPrev, q0, q1, q2, qL); }
+  }
   uint32_t lo, hi;
   pass_range<C>(P, g, tau, tauPrev, lo, hi);
   const uint32_t n = g.cHi - g.cLo;
   uint32_t flag = (hi <= lo) ? 0u : ((lo == 0 && hi == n) ? 1u : 2u);
-  double last = tau;
+  double last[3] = {tau, 0.0, 0.0};
   if (C::KIND == KIND_RECUR && flag) {
     // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
     // beyond |phase| ~ 2^18 that exceeds the 1e-9 parity budget, so such steps are evaluated
@@ -361,24 +426,68 @@ SRB_HD void prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint
   }
   sm.rng[lane] = lo | (hi << 10) | (flag << 30);
   st.nPass += hi - lo; st.nAll += n;
-  constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
 #pragma unroll
-  for (int k = 0; k < NV; k++) sm.rec[lane][k] = (TM)V[k];
-  sm.rec[lane][NV] = (TM)last;   // recurrence: 2cos(d) ; direct: tau
+  for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
+  sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau
+  if (C::KIND == KIND_RECUR) { sm.rec[lane][C::NV + 1] = (TM)last[1]; sm.rec[lane][C::NV + 2] = (TM)last[2]; }
+  return flag;
 }
 
 // -------------------------------------------------------------------------------- main phase
+// one full step of one tile: v0 = seedX, v1 = seedY, then the three-term recurrence
 template <class C>
-SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, int lane,
-                       ThreadState<C>& st) {
+SRB_HD void tile_step_full(const typename C::TM* V, typename C::TM coef, typename C::TM vm, typename C::TM v,
+                           ThreadState<C>& st) {
+  using TM = typename C::TM;
+  constexpr int TW = C::TW;
+  constexpr int NV = C::NV;
+#pragma unroll
+  for (int c = 0; c < NV; c++) st.acc[c] = fma(V[c], vm, st.acc[c]);
+#pragma unroll
+  for (int c = 0; c < NV; c++) st.acc[NV + c] = fma(V[c], v, st.acc[NV + c]);
+#pragma unroll
+  for (int k = 2; k < TW; k++) {
+    const TM vn = fma(coef, v, -vm); vm = v; v = vn;
+#pragma unroll
+    for (int c = 0; c < NV; c++) st.acc[k * NV + c] = fma(V[c], v, st.acc[k * NV + c]);
+  }
+}
+
+template <class C>
+SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, uint32_t fullMask,
+                       uint32_t anyMask, int lane, ThreadState<C>& st) {
   using TM = typename C::TM; using TI = typename C::TI;
   constexpr int TW = C::TW;
-  constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
+  constexpr int NV = C::NV;
   const int m = lane & 15;
+  const uint32_t sgn = (lane >> 4) ? 0u : 0x80000000u;   // cos lanes subtract s0*sd
+  const uint32_t allMask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+  if (fullMask == allMask) {
+    // hot path: every step of the sub-batch passes the guard at every node of the chunk.
+    // Operands of step s+1 are fetched from shared memory while step s is being accumulated.
+    TM R[NV + 3], nR[NV + 3], x, xo, nx, nxo;
+#pragma unroll
+    for (int k = 0; k < NV + 3; k++) R[k] = sm.rec[0][k];
+    x = sm.seeds[lane][0]; xo = sm.seeds[lane ^ 16][0];
+#pragma unroll 2
+    for (int s = 0; s < cnt; s++) {
+      const int sn = s + 1 < cnt ? s + 1 : s;
+#pragma unroll
+      for (int k = 0; k < NV + 3; k++) nR[k] = sm.rec[sn][k];
+      nx = sm.seeds[lane][sn]; nxo = sm.seeds[lane ^ 16][sn];
+      // second node of the tile: cos lane c1 = c0*cd - s0*sd ; sin lane s1 = s0*cd + c0*sd
+      const TM v1 = fma(xo, flipsign(R[NV + 2], sgn), x * R[NV + 1]);
+      tile_step_full<C>(R, R[NV], x, v1, st);
+#pragma unroll
+      for (int k = 0; k < NV + 3; k++) R[k] = nR[k];
+      x = nx; xo = nxo;
+    }
+    return;
+  }
   for (int s = 0; s < cnt; s++) {
+    if (!((anyMask >> s) & 1u)) continue;   // warp-uniform: nothing passes the guard at this step
     const uint32_t r = sm.rng[s];
     const uint32_t flag = r >> 30;
-    if (flag == 0) continue;          // warp-uniform: nothing passes the guard at this step
     TM V[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
@@ -400,18 +509,10 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
       }
       continue;
     }
-    TM vm = sm.seeds[lane][s], v = sm.seeds[32 + lane][s];
+    TM vm = sm.seeds[lane][s];
+    TM v = fma(sm.seeds[lane ^ 16][s], flipsign(sm.rec[s][NV + 2], sgn), vm * sm.rec[s][NV + 1]);
     if (flag == 1) {
-#pragma unroll
-      for (int c = 0; c < NV; c++) st.acc[c] = fma(V[c], vm, st.acc[c]);
-#pragma unroll
-      for (int c = 0; c < NV; c++) st.acc[NV + c] = fma(V[c], v, st.acc[NV + c]);
-#pragma unroll
-      for (int k = 2; k < TW; k++) {
-        const TM vn = fma(coef, v, -vm); vm = v; v = vn;
-#pragma unroll
-        for (int c = 0; c < NV; c++) st.acc[k * NV + c] = fma(V[c], v, st.acc[k * NV + c]);
-      }
+      tile_step_full<C>(V, coef, vm, v, st);
     } else {
       const int lo = (int)(r & 0x3ffu) - m * TW, hi = (int)((r >> 10) & 0x3ffu) - m * TW;
       if (hi <= 0 || lo >= TW) continue;
@@ -435,7 +536,7 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
                         ThreadState<C>& st) {
   using TM = typename C::TM;
   constexpr int TW = C::TW;
-  constexpr int NV = (C::MODE == MODE_FAR) ? 3 : 6;
+  constexpr int NV = C::NV;
   for (int s = 0; s < cnt; s++) {
     const uint32_t r = sm.rng[s];
     if ((r >> 30) == 0) continue;
@@ -453,9 +554,9 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
         if (C::NATIVE) sincos_native((float)ph, (float*)&sn, (float*)&cs); else sincos_t(ph, &sn, &cs);
         if (C::MODE == MODE_FAR) {
 #pragma unroll
-          for (int c = 0; c < 3; c++) {
-            st.acc[k * 6 + c] = fma(V[c], cs, st.acc[k * 6 + c]);
-            st.acc[k * 6 + 3 + c] = fma(V[c], sn, st.acc[k * 6 + 3 + c]);
+          for (int c = 0; c < C::NC; c++) {
+            st.acc[k * C::NPN + c] = fma(V[c], cs, st.acc[k * C::NPN + c]);
+            st.acc[k * C::NPN + C::NC + c] = fma(V[c], sn, st.acc[k * C::NPN + C::NC + c]);
           }
         } else {
           const TM t1 = st.wl[k] * sn, t2 = st.wl[k] * cs;
@@ -486,9 +587,10 @@ SRB_HD double* dest(const Params& P, uint32_t pc, int c) {
 template <class C>
 SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint32_t pc, uint32_t iSnap,
                        int lane, const ThreadState<C>* st) {
-  using TI = typename C::TI; using TM = typename C::TM;
+  using TI = typename C::TI;
   constexpr int TW = C::TW;
-  constexpr int NV = C::NACC / TW;
+  constexpr int NPN = C::NPN;
+  constexpr int NCF = (C::MODE == MODE_FAR) ? C::NC : 3;   // complex amplitude components held
 #if defined(__CUDA_ARCH__)
   const ThreadState<C>& me = st[0];
 #else
@@ -509,34 +611,46 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
     double re[3], im[3];
     if (C::KIND == KIND_DIRECT) {
 #pragma unroll
-      for (int c = 0; c < 3; c++) { re[c] = (double)me.acc[k * 6 + c]; im[c] = (double)me.acc[k * 6 + 3 + c]; }
+      for (int c = 0; c < NCF; c++) { re[c] = (double)me.acc[k * NPN + c]; im[c] = (double)me.acc[k * NPN + NCF + c]; }
     } else {
-      double ma[NV], pa[NV];
+      double ma[NPN], pa[NPN];
 #pragma unroll
-      for (int c = 0; c < NV; c++) {
-        ma[c] = (double)me.acc[k * NV + c];
+      for (int c = 0; c < NPN; c++) {
+        ma[c] = (double)me.acc[k * NPN + c];
 #if defined(__CUDA_ARCH__)
         pa[c] = __shfl_xor_sync(0xffffffffu, ma[c], 16);
 #else
-        pa[c] = (double)st[lane ^ 16].acc[k * NV + c];
+        pa[c] = (double)st[lane ^ 16].acc[k * NPN + c];
 #endif
       }
       const double* cosS = part ? pa : ma;
       const double* sinS = part ? ma : pa;
       if (C::MODE == MODE_FAR) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) { re[c] = cosS[c]; im[c] = sinS[c]; }
+        for (int c = 0; c < NCF; c++) { re[c] = cosS[c]; im[c] = sinS[c]; }
       } else {
         // near: acc = {P = sum B*v, Q = sum Cv*v}; Re = Qcos - w*Psin, Im = Qsin + w*Pcos
         const double wj = valid ? (double)((const TI*)P.omega)[j] : 0.0;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          re[c] = cosS[(NV > 3 ? 3 : 0) + c] - wj * sinS[c];
-          im[c] = sinS[(NV > 3 ? 3 : 0) + c] + wj * cosS[c];
+          re[c] = cosS[(NPN > 3 ? 3 : 0) + c] - wj * sinS[c];
+          im[c] = sinS[(NPN > 3 ? 3 : 0) + c] + wj * cosS[c];
         }
       }
     }
     if (!valid) continue;
+    if (C::MODE == MODE_FAR && C::NC == 2) {
+      if (P.comp == COMP_TOTAL) {
+        // |F|^2 in the orthonormal transverse basis
+        if (part == 0)
+          dest<C>(P, pc, 0)[idx] += wpdt2 * ((re[0] * re[0] + re[1] * re[1]) + (im[0] * im[0] + im[1] * im[1]));
+        continue;
+      }
+      // Cartesian components F = F_theta e_theta + F_phi e_phi
+      const double rt = re[0], rp = re[1], it_ = im[0], ip = im[1];
+      re[0] = rt * g.tx + rp * g.px; re[1] = rt * g.ty + rp * g.py; re[2] = rt * g.tz + rp * g.pz;
+      im[0] = it_ * g.tx + ip * g.px; im[1] = it_ * g.ty + ip * g.py; im[2] = it_ * g.tz + ip * g.pz;
+    }
     if (!cplx) {
       if (part == 0) {
         if (P.comp == COMP_TOTAL) {
@@ -617,6 +731,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
     tv.n = (uint32_t)(P.offsets[t + 1] - o);
     tv.x = (const TI*)P.x + o; tv.y = (const TI*)P.y + o; tv.z = (const TI*)P.z + o;
     tv.ux = (const TI*)P.ux + o; tv.uy = (const TI*)P.uy + o; tv.uz = (const TI*)P.uz + o;
+    tv.pre = P.pre ? P.pre + o : nullptr;
     tv.itStart = P.itStart[t]; tv.itEnd = P.itEnd[t];
     tv.snaps = P.itSnaps + (size_t)P.snapStride * t;
     tv.w = ldv<TI>(P.w, t);
@@ -637,11 +752,19 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
       const uint32_t stop = (uint32_t)(itf + 1) < nComp ? (uint32_t)(itf + 1) : nComp;
       for (uint32_t base = cur; base < stop; base += SUB) {
         const int cnt = (int)(stop - base < (uint32_t)SUB ? stop - base : (uint32_t)SUB);
+        uint32_t fullMask = 0u, anyMask = 0u;   // bit s: step s of the sub-batch is all-pass / has any pass
         SRB_LANES_BEGIN
-          prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);
+          const uint32_t fl = prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);
+#if defined(__CUDA_ARCH__)
+          fullMask = __ballot_sync(0xffffffffu, fl == 1u);
+          anyMask = __ballot_sync(0xffffffffu, fl != 0u);
+#else
+          if (fl == 1u) fullMask |= 1u << lane;
+          if (fl != 0u) anyMask |= 1u << lane;
+#endif
         SRB_LANES_END
         SRB_LANES_BEGIN
-          if (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, lane, SRB_ST);
+          if (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, lane, SRB_ST);
         SRB_LANES_END
       }

@@ -31,7 +31,7 @@ static void run_all(const Params& P0, unsigned long long* counters) {
 }
 
 extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int nOut,
-                                 int kind, int tw, uint32_t nPC, unsigned long long* counters) {
+                                 int kind, int tw, uint32_t nPC, unsigned long long* counters, int prepass) {
   Params P;
   std::memset(&P, 0, sizeof P);
   P.mode = g->mode; P.comp = g->comp;
@@ -55,18 +55,45 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   const size_t perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
   std::vector<double> slabs((size_t)(nPC > 1 ? nPC - 1 : 0) * perOut * nOut, 0.0);
   P.slabs = slabs.data(); P.slabStride = perOut * nOut; P.nPC = nPC;
+  // optional pre-pass planes (same code path the GPU pre-pass kernel uses)
+  std::vector<double> pre;
+  if (prepass && t->nTracks) {
+    const uint64_t total = t->totalSteps_host;
+    pre.assign((size_t)(g->mode == SRB_MODE_FAR ? 6 : 3) * total, 0.0);
+    const double dtInv = sdiv(1.0, g->dt);
+    for (uint32_t tr = 0; tr < t->nTracks; tr++) {
+      const uint64_t o = t->offsets[tr], n = t->offsets[tr + 1] - o;
+      for (uint64_t it = 0; it < n; it++) {
+        const uint64_t i = o + it;
+        if (g->mode == SRB_MODE_FAR) {
+          double av[3] = {0, 0, 0}, bv[3] = {0, 0, 0};
+          if (it + 1 < n) far_step_kinematics<double>(t->ux, t->uy, t->uz, i, dtInv, av, bv);
+          for (int c = 0; c < 3; c++) { pre[c * total + i] = av[c]; pre[(3 + c) * total + i] = bv[c]; }
+        } else {
+          double bv[3];
+          near_step_kinematics<double>(t->ux, t->uy, t->uz, i, bv);
+          for (int c = 0; c < 3; c++) pre[c * total + i] = bv[c];
+        }
+      }
+    }
+    P.pre = pre.data(); P.preStride = total;
+  }
   const bool f32 = g->dtype == SRB_DTYPE_F32;
   bool ok = false;
-#define EMU_CASE(K, M, TWV)                                                                     \
-  if (kind == K && g->mode == M && tw == TWV) {                                                 \
-    if (f32) run_all<Cfg<double, float, M, K, TWV, false>>(P, counters);                         \
-    else run_all<Cfg<double, double, M, K, TWV, false>>(P, counters);                           \
+  const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
+  const int nc = (kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
+#define EMU_CASE1(K, M, TWV, NCV)                                                               \
+  if (kind == K && g->mode == M && tw == TWV && nc == NCV) {                                    \
+    if (f32) run_all<Cfg<double, float, M, K, TWV, false, NCV>>(P, counters);                   \
+    else run_all<Cfg<double, double, M, K, TWV, false, NCV>>(P, counters);                      \
     ok = true; }
+#define EMU_CASE(K, M, TWV) EMU_CASE1(K, M, TWV, 2) EMU_CASE1(K, M, TWV, 3)
   EMU_CASE(KIND_RECUR, MODE_FAR, 16) EMU_CASE(KIND_RECUR, MODE_FAR, 8) EMU_CASE(KIND_RECUR, MODE_FAR, 4)
   EMU_CASE(KIND_RECUR, MODE_NEAR, 8) EMU_CASE(KIND_RECUR, MODE_NEAR, 4) EMU_CASE(KIND_RECUR, MODE_NEAR, 2)
   EMU_CASE(KIND_DIRECT, MODE_FAR, 8) EMU_CASE(KIND_DIRECT, MODE_FAR, 4) EMU_CASE(KIND_DIRECT, MODE_FAR, 2)
   EMU_CASE(KIND_DIRECT, MODE_NEAR, 8) EMU_CASE(KIND_DIRECT, MODE_NEAR, 4) EMU_CASE(KIND_DIRECT, MODE_NEAR, 2)
 #undef EMU_CASE
+#undef EMU_CASE1
   if (!ok) return -1;
   for (uint32_t s = 0; s + 1 < nPC; s++)
     for (int c = 0; c < nOut; c++)
