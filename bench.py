@@ -87,8 +87,10 @@ def cpu_port_rate(n_particles, n_steps, threads=None):
     from oracle import reference_path as rp
     from synchrad_b200 import synthetic
     rp.build()
-    if threads:
-        os.environ['OMP_NUM_THREADS'] = str(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (libgomp reads the
+    # variable when the oracle library is first loaded)
+    os.environ['OMP_NUM_THREADS'] = str(threads or os.cpu_count())
+    rp.set_threads(threads or os.cpu_count())
     batch = synthetic.c5_batch(n_particles, n_steps, seed=4321, device='cpu')
     tracks = synthetic.batch_to_track_list(batch)
     args = synthetic.c5_args(GRID)

@@ -52,6 +52,15 @@ def build(force=False):
 _libs = {}
 
 
+def set_threads(n):
+    """OpenMP threads of the oracle kernels (torchrun exports OMP_NUM_THREADS=1 and libgomp reads it
+    when first loaded, usually by torch; this sets the runtime value afterwards)."""
+    try:
+        ctypes.CDLL('libgomp.so.1').omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def _lib(kind='strict'):
     if kind not in _libs:
         path = os.path.join(_HERE, f'liboracle_{kind}.so')

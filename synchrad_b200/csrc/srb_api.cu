@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -209,9 +210,13 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   const int tiles = p->kind == KIND_RECUR ? 16 : 32;
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
-  else { twMax = 8; twMin = 2; }
+  else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }
+  if (const char* f = std::getenv("SRB_FORCE_TW")) {        // tuning aid
+    const int tw = std::atoi(f);
+    if (tw >= twMin && tw <= twMax && (tw & (tw - 1)) == 0) p->tw = tw;
+  }
   const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
   p->nc = (p->kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
   if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L)) return fail("internal: no kernel for this configuration");

@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define SRB_HD __host__ __device__ __forceinline__
@@ -99,31 +100,6 @@ SRB_HD void sincos_d(double x, double* s, double* c) {
   *s = sin(x); *c = cos(x);
 #endif
 }
-// sin/cos of a double of ANY magnitude at fast-path cost: x/pi is formed as an exact
-// double-double product, reduced mod 2 exactly, and handed to sincospi (whose own reduction is
-// exact).  Near-field phases omega*(t+R) reach 1e10 rad and SI-unit far-field phases 1e6
-// (SURVEY §7), far beyond the fast path of CUDA's sincos().  Absolute phase error ~1e-15 rad.
-SRB_HD void sincos_big(double x, double* s, double* c) {
-#if defined(__CUDA_ARCH__)
-  const double h = __dmul_rn(x, 0.3183098861837907);
-  double l = __fma_rn(x, 0.3183098861837907, -h);
-  l = __fma_rn(x, -1.9678676675182486e-17, l);
-  const double n = __dsub_rn(__fma_rn(h, 0.5, 6755399441055744.0), 6755399441055744.0);  // rint(h/2)
-  const double f = __dadd_rn(__fma_rn(n, -2.0, h), l);
-  sincospi(f, s, c);
-#else
-  *s = sin(x); *c = cos(x);
-#endif
-}
-SRB_HD void sincos_t(double x, double* s, double* c) { sincos_big(x, s, c); }
-SRB_HD double tmul(double a, double b) { return smul(a, b); }
-SRB_HD float tmul(float a, float b) {
-#if defined(__CUDA_ARCH__)
-  return __fmul_rn(a, b);
-#else
-  return a * b;
-#endif
-}
 // v with its sign bit XOR-ed by mask (0 or 0x80000000): a lane-dependent sign without an FP64-pipe op
 SRB_HD double flipsign(double v, uint32_t mask) {
 #if defined(__CUDA_ARCH__)
@@ -137,6 +113,53 @@ SRB_HD float flipsign(float v, uint32_t mask) {
   return __int_as_float(__float_as_int(v) ^ (int)mask);
 #else
   return mask ? -v : v;
+#endif
+}
+// sin/cos of a double of ANY magnitude (|x| < 2^50) at fast-path cost, FP64 pipe only (no FRND /
+// F2I conversions, which run at 1/4 rate).  Near-field phases omega*(t+R) reach 1e10 rad and
+// SI-unit far-field phases 1e6, far beyond the fast path of CUDA's sincos().
+//   x/pi = h + l as an exact double-double product; q = rint(2(h+l)) by the magic-number trick
+//   (the quadrant is read from the mantissa); r = (h - q/2) + l in [-1/4, 1/4]; y = pi*r;
+//   fdlibm's __kernel_sin/__kernel_cos minimax polynomials on [-pi/4, pi/4].
+// Max abs error 2.0e-16 for |x| up to 1e13 (checked against sinl/cosl, tests/test_emulated_kernels.py).
+SRB_HD void sincos_big(double x, double* sn, double* cs) {
+  const double h = smul(x, 0.3183098861837907);
+  double l = fma(x, 0.3183098861837907, -h);
+  l = fma(x, -1.9678676675182486e-17, l);
+  const double t = fma(h, 2.0, 6755399441055744.0);
+  const double qd = ssub(t, 6755399441055744.0);
+#if defined(__CUDA_ARCH__)
+  const uint32_t q = (uint32_t)__double2loint(t);
+#else
+  uint64_t tb; memcpy(&tb, &t, 8);
+  const uint32_t q = (uint32_t)tb;
+#endif
+  const double r = sadd(fma(qd, -0.5, h), l);
+  const double y = fma(r, 3.141592653589793, smul(r, 1.2246467991473532e-16));
+  const double z = smul(y, y);
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(smul(y, z), ps, y);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double c = fma(smul(z, z), pc, fma(z, -0.5, 1.0));
+  const double a = (q & 1u) ? c : s, b = (q & 1u) ? s : c;
+  *sn = flipsign(a, (q & 2u) << 30);
+  *cs = flipsign(b, ((q + 1u) & 2u) << 30);
+}
+SRB_HD void sincos_t(double x, double* s, double* c) { sincos_big(x, s, c); }
+SRB_HD double tmul(double a, double b) { return smul(a, b); }
+SRB_HD float tmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
 #endif
 }
 SRB_HD void sincos_t(float x, float* s, float* c) {
@@ -532,14 +555,48 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
 
 // Direct main phase: lane = tile of TW nodes, per-node sincos of the reference's rounded phase.
 template <class C>
-SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, int lane,
-                        ThreadState<C>& st) {
+SRB_HD void direct_update(const typename C::TM* V, typename C::TM w, typename C::TM tau, int k, ThreadState<C>& st) {
+  using TM = typename C::TM;
+  TM sn, cs;
+  const TM ph = tmul(w, tau);  // single rounding == the reference's omega*(time - n.r)
+  if (C::NATIVE) sincos_native((float)ph, (float*)&sn, (float*)&cs); else sincos_t(ph, &sn, &cs);
+  if (C::MODE == MODE_FAR) {
+#pragma unroll
+    for (int c = 0; c < C::NC; c++) {
+      st.acc[k * C::NPN + c] = fma(V[c], cs, st.acc[k * C::NPN + c]);
+      st.acc[k * C::NPN + C::NC + c] = fma(V[c], sn, st.acc[k * C::NPN + C::NC + c]);
+    }
+  } else {
+    const TM t1 = w * sn, t2 = w * cs;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {   // Re += -c1*sin + c2*cos ; Im += c1*cos + c2*sin
+      st.acc[k * 6 + c] = fma(V[3 + c], cs, fma(-V[c], t1, st.acc[k * 6 + c]));
+      st.acc[k * 6 + 3 + c] = fma(V[3 + c], sn, fma(V[c], t2, st.acc[k * 6 + 3 + c]));
+    }
+  }
+}
+
+template <class C>
+SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, uint32_t fullMask,
+                        uint32_t anyMask, int lane, ThreadState<C>& st) {
   using TM = typename C::TM;
   constexpr int TW = C::TW;
   constexpr int NV = C::NV;
+  const uint32_t allMask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+  if (fullMask == allMask) {       // every node of the chunk passes at every step: no predicates
+    for (int s = 0; s < cnt; s++) {
+      TM V[NV];
+#pragma unroll
+      for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
+      const TM tau = sm.rec[s][NV];
+#pragma unroll
+      for (int k = 0; k < TW; k++) direct_update<C>(V, st.wl[k], tau, k, st);
+    }
+    return;
+  }
   for (int s = 0; s < cnt; s++) {
+    if (!((anyMask >> s) & 1u)) continue;
     const uint32_t r = sm.rng[s];
-    if ((r >> 30) == 0) continue;
     const int lo = (int)(r & 0x3ffu) - lane * TW, hi = (int)((r >> 10) & 0x3ffu) - lane * TW;
     if (hi <= 0 || lo >= TW) continue;
     TM V[NV];
@@ -547,27 +604,8 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
     const TM tau = sm.rec[s][NV];
 #pragma unroll
-    for (int k = 0; k < TW; k++) {
-      if (k >= lo && k < hi) {
-        TM sn, cs;
-        const TM ph = tmul(st.wl[k], tau);  // single rounding == the reference's omega*(time - n.r)
-        if (C::NATIVE) sincos_native((float)ph, (float*)&sn, (float*)&cs); else sincos_t(ph, &sn, &cs);
-        if (C::MODE == MODE_FAR) {
-#pragma unroll
-          for (int c = 0; c < C::NC; c++) {
-            st.acc[k * C::NPN + c] = fma(V[c], cs, st.acc[k * C::NPN + c]);
-            st.acc[k * C::NPN + C::NC + c] = fma(V[c], sn, st.acc[k * C::NPN + C::NC + c]);
-          }
-        } else {
-          const TM t1 = st.wl[k] * sn, t2 = st.wl[k] * cs;
-#pragma unroll
-          for (int c = 0; c < 3; c++) {   // Re += -c1*sin + c2*cos ; Im += c1*cos + c2*sin
-            st.acc[k * 6 + c] = fma(V[3 + c], cs, fma(-V[c], t1, st.acc[k * 6 + c]));
-            st.acc[k * 6 + 3 + c] = fma(V[3 + c], sn, fma(V[c], t2, st.acc[k * 6 + 3 + c]));
-          }
-        }
-      }
-    }
+    for (int k = 0; k < TW; k++)
+      if (k >= lo && k < hi) direct_update<C>(V, st.wl[k], tau, k, st);
   }
 }
 
@@ -765,7 +803,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
         SRB_LANES_END
         SRB_LANES_BEGIN
           if (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
-          else main_direct<C>(P, g, sm, cnt, lane, SRB_ST);
+          else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
       }
       SRB_LANES_BEGIN

@@ -3,7 +3,7 @@
 // It exists so the kernel LOGIC (flush chains, pass ranges, seeds, recurrences, tile indexing)
 // can be debugged against the oracle in a container without a GPU.  It is not a fallback: the
 // product package never loads it and fails loudly without the CUDA library.
-// Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC -o tests/emu/libsrb_emu.so tests/emu/emu.cpp
+// Build: g++ -O2 -mfma -ffp-contract=off -fopenmp -shared -fPIC -o tests/emu/libsrb_emu.so tests/emu/emu.cpp
 #include <cstring>
 #include <vector>
 
@@ -28,6 +28,11 @@ static void run_all(const Params& P0, unsigned long long* counters) {
     tot[0] += cnt[0]; tot[1] += cnt[1];
   }
   if (counters) { counters[0] = tot[0]; counters[1] = tot[1]; }
+}
+
+// exposes the device sincos for accuracy tests
+extern "C" void srb_emu_sincos(const double* x, double* s, double* c, long n) {
+  for (long i = 0; i < n; i++) sincos_big(x[i], s + i, c + i);
 }
 
 extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int nOut,

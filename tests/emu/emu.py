@@ -18,7 +18,7 @@ _SRC = [os.path.join(_HERE, 'emu.cpp'),
 def build():
     if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in _SRC):
         return
-    subprocess.check_call(['/usr/bin/g++', '-std=c++17', '-O2', '-ffp-contract=off', '-fopenmp',
+    subprocess.check_call(['/usr/bin/g++', '-std=c++17', '-O2', '-mfma', '-ffp-contract=off', '-fopenmp',
                            '-shared', '-fPIC', '-o', _SO, _SRC[0]])
 
 

@@ -108,3 +108,24 @@ def test_float_mixed_precision_is_no_worse_than_literal_fp32(oracle):
         e = rel_errors(rad['total'], r64)
         assert e[0] <= e_lit[0] and e[1] <= e_lit[1], (kind, e, e_lit)
         assert max(e) < 2e-4, (kind, e)
+
+
+def test_device_sincos_accuracy():
+    """srb_core.cuh:sincos_big (host build of the same code) against long-double sin/cos."""
+    import ctypes
+    emu.build()
+    lib = ctypes.CDLL(emu._SO)
+    rs = np.random.RandomState(0)
+    for scale in (1.0, 1e3, 1e6, 1e10, 1e13):
+        x = np.ascontiguousarray(rs.uniform(-scale, scale, 200000))
+        s, c = np.empty_like(x), np.empty_like(x)
+        lib.srb_emu_sincos(x.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p),
+                           c.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(x.size))
+        xl = x.astype(np.longdouble)
+        assert np.abs(s - np.sin(xl)).max() < 3e-16 and np.abs(c - np.cos(xl)).max() < 3e-16, scale
+    x = np.array([0.0, np.pi / 2, -np.pi / 2, np.pi, 1e-300])
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib.srb_emu_sincos(x.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p),
+                       c.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(x.size))
+    np.testing.assert_allclose(s, [0, 1, -1, 0, 1e-300], atol=2e-16)
+    np.testing.assert_allclose(c, [1, 0, 0, -1, 1], atol=2e-16)
