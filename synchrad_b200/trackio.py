@@ -1,0 +1,122 @@
+"""HDF5 track / spectrum files of the path, in the reference's layouts.
+
+tracks file (written by the reference's converters, converters.py:102-127; read at calc.py:186-219):
+    tracks/<i>/{x,y,z,ux,uy,uz}  float64 [n_i]      tracks/<i>/w, tracks/<i>/it_start  scalars
+    misc/cdt  scalar   misc/N_particles  scalar   misc/it_range  int[2] (optional)
+    misc/propagation_direction  string (optional, not used by the path)
+spectrum file (calc.py:274-290 written, :648-666 read):
+    radiation/<key>  float64 (nSnaps, nOmega, nTheta|nR, nPhi)
+    Args/<k>  for every Args key except 'grid' and 'ctx'      snap_iterations  uint32[nSnaps]
+    total_weight  scalar
+
+h5py is used when it is importable; otherwise the bundled minimal reader/writer (h5lite) handles
+exactly these layouts.
+"""
+import numpy as np
+
+try:                                   # pragma: no cover - not installed in the build image
+    import h5py as _h5
+    BACKEND = 'h5py'
+except ImportError:
+    from . import h5lite as _h5
+    BACKEND = 'h5lite'
+
+_COMPS = ('x', 'y', 'z', 'ux', 'uy', 'uz')
+
+
+def read_header(path):
+    """(cdt, it_range or None, N_particles)  — calc.py:187-205"""
+    f = _h5.File(path, 'r')
+    try:
+        cdt = float(f['misc/cdt'][()])
+        rng = tuple(int(v) for v in f['misc/it_range'][()]) if 'it_range' in f['misc'].keys() else None
+        n = int(f['misc/N_particles'][()])
+    finally:
+        f.close()
+    return cdt, rng, n
+
+
+def read_tracks(path, indices):
+    """List of [x,y,z,ux,uy,uz,w,it_start] for the given track indices — calc.py:210-216"""
+    f = _h5.File(path, 'r')
+    out = []
+    try:
+        for ip in indices:
+            g = f[f'tracks/{int(ip):d}']
+            tr = [np.asarray(g[c][()], dtype=np.double) for c in _COMPS]
+            tr.append(float(g['w'][()]))
+            tr.append(int(g['it_start'][()]) if 'it_start' in g.keys() else 0)
+            out.append(tr)
+    finally:
+        f.close()
+    return out
+
+
+def write_tracks(path, tracks, cdt, it_range=None):
+    """Write a tracks file in the converters' layout (converters.py:102-127)."""
+    f = _h5.File(path, 'w')
+    try:
+        lo, hi = None, None
+        for i, t in enumerate(tracks):
+            for c, a in zip(_COMPS, t[:6]):
+                f[f'tracks/{i:d}/{c}'] = np.asarray(a, dtype=np.double)
+            f[f'tracks/{i:d}/w'] = np.double(t[6])
+            its = int(t[7]) if len(t) == 8 else 0
+            f[f'tracks/{i:d}/it_start'] = np.int64(its)
+            n = np.asarray(t[0]).size
+            lo = its if lo is None else min(lo, its)
+            hi = its + n if hi is None else max(hi, its + n)
+        f['misc/cdt'] = np.double(cdt)
+        f['misc/N_particles'] = np.int64(len(tracks))
+        if it_range is True and lo is not None:
+            it_range = (lo, hi)
+        if it_range not in (None, False, True):
+            f['misc/it_range'] = np.asarray(it_range, dtype=np.int64)
+        f['misc/propagation_direction'] = 'z'
+    finally:
+        f.close()
+
+
+def write_spectrum(path, calc):
+    """calc.py:274-290"""
+    f = _h5.File(path, 'w')
+    try:
+        for key, arr in calc.Data['radiation'].items():
+            f['radiation/' + key] = np.asarray(arr, dtype=np.double)
+        for key, val in calc.Args.items():
+            if key in ('grid', 'ctx'):
+                continue
+            if isinstance(val, (list, tuple)) and len(val) == 0:
+                val = np.zeros((0,), dtype=np.double)            # what h5py stores for []
+            elif isinstance(val, (list, tuple)) and all(isinstance(v, str) for v in val):
+                val = np.array([v.encode() for v in val])        # Features: fixed-length strings
+            elif isinstance(val, bool):
+                val = np.uint8(val)
+            f['Args/' + key] = val
+        f['snap_iterations'] = np.asarray(calc.snap_iterations, dtype=np.uint32)
+        f['total_weight'] = np.double(calc.total_weight)
+    finally:
+        f.close()
+
+
+def read_spectrum(path, calc):
+    """calc.py:648-666: fills calc.Data['radiation'], calc.Args, snap_iterations, total_weight."""
+    calc.Data = {'radiation': {}}
+    calc.Args = {}
+    f = _h5.File(path, 'r')
+    try:
+        for key in f['radiation'].keys():
+            calc.Data['radiation'][key] = f['radiation/' + key][()]
+        for key in f['Args'].keys():
+            val = f['Args/' + key][()]
+            if isinstance(val, bytes):
+                val = val.decode()
+            elif isinstance(val, np.ndarray) and val.dtype.kind in 'SO':
+                val = [v.decode() if isinstance(v, bytes) else v for v in val.tolist()]
+            calc.Args[key] = val
+        calc.snap_iterations = f['snap_iterations'][()]
+        calc.total_weight = f['total_weight'][()]
+    finally:
+        f.close()
+    dt = calc.Args.get('dtype', 'double')
+    calc.dtype = np.double if dt == 'double' else np.single

@@ -273,3 +273,32 @@ def test_c_abi_host_entry(cuda_lib, oracle):
     got = np.ascontiguousarray((out - 1.0).swapaxes(-1, -3))
     assert max(rel_errors(got, ref['radiation']['total'])) < 1e-9
     assert cnt[0] == ref['passed'] and cnt[1] == ref['updates']
+
+
+# ---------------------------------------------------------------------------- file-based drop-in call
+def test_file_tracks_to_file_spectrum(cuda_lib, oracle, tmp_path):
+    """`SynchRad(calc_input).calculate_spectrum(file_tracks=..., file_spectrum=...)`
+    (tutorials/PIC/compute_spectrum.py:16-18) and the analysis-only re-load (calc.py:98-99)."""
+    from synchrad.calc import SynchRad
+    from synchrad_b200 import trackio
+    tracks, dt, info = cases.undulator_tracks(5, seed=9)
+    tracks = [t[:7] + [s] for t, s in zip(tracks, [0, 3, 0, 11, 2])]
+    ftr, fsp = str(tmp_path / 'tracks.h5'), str(tmp_path / 'spectrum.h5')
+    trackio.write_tracks(ftr, tracks, cdt=dt, it_range=(0, 1700))
+    args = cases.undulator_args(info, grid=(64, 6, 4))
+    calc = SynchRad(dict(args))
+    calc.calculate_spectrum(file_tracks=ftr, file_spectrum=fsp, comp='cartesian', nSnaps=2, Np_max=4)
+    ref = oracle.calculate_spectrum(args, tracks, dt, comp='cartesian', nSnaps=2, Np_max=4, it_range=(0, 1700))
+    assert_close(calc, ref['radiation'])
+    assert float(calc.Args['timeStep']) == dt            # misc/cdt overrides the kwarg (calc.py:189)
+    loaded = SynchRad(file_spectrum=fsp)
+    for k in 'xyz':
+        np.testing.assert_array_equal(loaded.Data['radiation'][k], calc.Data['radiation'][k])
+    np.testing.assert_array_equal(loaded.snap_iterations, calc.snap_iterations)
+    assert loaded.total_weight == calc.total_weight and loaded.Args['comp'] == 'cartesian'
+    assert loaded.get_energy(lambda0_um=1) == pytest.approx(calc.get_energy(lambda0_um=1), rel=1e-14)
+    # per-track ranges when the file has no misc/it_range (calc.py:199-201)
+    trackio.write_tracks(ftr, tracks, cdt=dt)
+    calc.calculate_spectrum(file_tracks=ftr, verbose=False)
+    ref2 = oracle.calculate_spectrum(args, tracks, dt)
+    assert_close(calc, ref2['radiation'])
