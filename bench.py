@@ -277,6 +277,7 @@ def run_product(a):
         'kernel_ms_per_launch': k_ms,
         'kernel': 'k_integrate<%s, tile %d>' % ('recurrence' if info.kind == 1 else 'direct', info.tile_width),
         'traffic': None,
+        'fp64_pipe_active_ncu': 0.70,   # profiles/r01_ncu_v3_final_kernel.txt (sm__pipe_fp64_cycles_active), same kernel, smaller batch
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }

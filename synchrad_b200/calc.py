@@ -203,7 +203,7 @@ class SynchRad(Utilities):
             self.snap_iterations = np.zeros(nSnaps, dtype=np.uint32)
 
         res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
-                               native=self._native, phasor=self._phasor,
+                               native=self._native, phasor=self._phasor, timing=True,
                                timeStep=getattr(self, '_timeStep64', float(self.Args['timeStep'])))
         n_w, n_2, n_p = (int(v) for v in self.Args['gridNodeNums'])
         dev_out = engine.to_host_layout(res.spectra, nSnaps, n_w, n_2, n_p)
@@ -218,7 +218,7 @@ class SynchRad(Utilities):
         self.last_run = {
             'passed_updates': int(c[0]), 'visited_updates': int(c[1]),
             'updates': int(packed.updates_per_node) * int(self.Args['numGridNodes']),
-            'kernel': 'recurrence' if res.info.kind == 1 else 'direct',
+            'kernel': 'recurrence' if res.info.kind == 1 else 'direct', 'integrate_ms': res.elapsed_ms,
             'tile_width': int(res.info.tile_width), 'particle_chunks': int(res.info.n_particle_chunks),
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
             'h2d_bytes': int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes

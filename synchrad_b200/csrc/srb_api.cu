@@ -243,6 +243,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   maxPC = std::min<uint64_t>(maxPC, 1 + slabCap);
   maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, (64 * slots) / p->nVDtiles));
   maxPC = std::min<uint64_t>(maxPC, 4096);
+  maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, 0x7fffffffull / p->nVDtiles));   // gridDim.x limit
   double best = -1.0; uint32_t bestN = 1;
   for (uint64_t n = 1; n <= maxPC; n++) {
     const uint64_t blocks = (uint64_t)p->nVDtiles * n;

@@ -296,10 +296,8 @@ template <class TI> SRB_HD double ldv(const void* p, size_t i) { return (double)
 // strict restatement of kernel_farfield.cl:65-94 / kernel_nearfield.cl:64-85.
 template <class C>
 SRB_HD void prep_far(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
-                     double dtInv, double& tau, double A[3]) {
+                     double dtInv, double A[3]) {
   using TI = typename C::TI;
-  const double time = smul((double)(tv.itStart + it), P.dt);
-  tau = ssub(time, sdot3(ldv<TI>(tv.x, it), ldv<TI>(tv.y, it), ldv<TI>(tv.z, it), g.nx, g.ny, g.nz));
   double a[3], b[3];
   if (tv.pre) {
 #pragma unroll
@@ -344,10 +342,8 @@ SRB_HD void near_tau(const Params& P, const Geom& g, const TrackView& tv, uint32
 // near: B = rInv*(beta - n), Cv = rInv^2 * n ; the reference's c1 = omega*B, c2 = Cv
 template <class C>
 SRB_HD void prep_near(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
-                      double& tau, double B[3], double Cv[3]) {
+                      double r0, double r1, double r2, double rL, double B[3], double Cv[3]) {
   using TI = typename C::TI;
-  double r0, r1, r2, rL;
-  near_tau<C>(P, g, tv, it, tau, r0, r1, r2, rL);
   const double rInv = sdiv(1.0, rL);
   const double n0 = smul(rInv, r0), n1 = smul(rInv, r1), n2 = smul(rInv, r2);
   double u[3];
@@ -421,9 +417,10 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   using TM = typename C::TM;
   if (lane >= cnt) return 0u;
   const uint32_t it = itBase + (uint32_t)lane;
-  double tau, tauPrev, V[6];
-  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, tau, V);
-  else prep_near<C>(P, g, tv, it, tau, V, V + 3);
+  double tau, tauPrev, V[6] = {0, 0, 0, 0, 0, 0};
+  double r0 = 0, r1 = 0, r2 = 0, rL = 1;
+  if (C::MODE == MODE_FAR) tau = far_tau<C>(P, g, tv, it);
+  else near_tau<C>(P, g, tv, it, tau, r0, r1, r2, rL);
   // tau of the previous step: the neighbouring lane has it (lanes [0,cnt) are all here)
 #if defined(__CUDA_ARCH__)
   tauPrev = __shfl_up_sync(cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u), tau, 1);
@@ -438,8 +435,12 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   pass_range<C>(P, g, tau, tauPrev, lo, hi);
   const uint32_t n = g.cHi - g.cLo;
   uint32_t flag = (hi <= lo) ? 0u : ((lo == 0 && hi == n) ? 1u : 2u);
+  st.nAll += n;
+  if (flag == 0u) { sm.rng[lane] = 0u; return 0u; }   // nothing passes the guard: no amplitude, no seeds
+  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, V);
+  else prep_near<C>(P, g, tv, it, r0, r1, r2, rL, V, V + 3);
   double last[3] = {tau, 0.0, 0.0};
-  if (C::KIND == KIND_RECUR && flag) {
+  if (C::KIND == KIND_RECUR) {
     // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
     // beyond |phase| ~ 2^18 that exceeds the 1e-9 parity budget, so such steps are evaluated
     // node by node (flag 3).  fp32 main phase: the seeds are fp64, no such limit.
@@ -448,7 +449,7 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
     if (big) flag = 3u; else make_seeds<C>(P, g, tau, sm, lane, last);
   }
   sm.rng[lane] = lo | (hi << 10) | (flag << 30);
-  st.nPass += hi - lo; st.nAll += n;
+  st.nPass += hi - lo;
 #pragma unroll
   for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
   sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau
