@@ -259,6 +259,10 @@ def run_product(a):
         return
 
     k_ms = sum(kernel_ms) / len(kernel_ms)
+    # DRAM bytes of ONE launch of this exact configuration, from an ncu capture of the same kernel
+    # (profiles/r01_ncu_full_size_launch_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum)
+    default_cfg = (a.dtype == 'double' and a.phasor == 'auto' and n_p == 12500 and n_s == 10000)
+    traffic = 26169446912 + 1634786304 if default_cfg else None
     slots_alg = ALG_SLOTS[a.dtype]
     achieved = updates_rank * slots_alg / (k_ms * 1e-3)          # algorithmic slots/s of one launch
     issued = None
@@ -276,8 +280,8 @@ def run_product(a):
         'frac_issued_main_loop': (updates_rank * issued / (k_ms * 1e-3) / peak.value) if issued else None,
         'kernel_ms_per_launch': k_ms,
         'kernel': 'k_integrate<%s, tile %d>' % ('recurrence' if info.kind == 1 else 'direct', info.tile_width),
-        'traffic': None,
-        'fp64_pipe_active_ncu': 0.70,   # profiles/r01_ncu_v3_final_kernel.txt (sm__pipe_fp64_cycles_active), same kernel, smaller batch
+        'traffic': traffic,
+        'fp64_pipe_active_ncu': 0.711 if default_cfg else None,   # sm__pipe_fp64_cycles_active, same file
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }
