@@ -13,7 +13,9 @@
 //                     for uniform omega grids, phasor seeds for 16 omega-tiles — is computed ONCE per
 //                     (direction, step), in the reference's exact operation order and without FMA
 //                     contraction (SURVEY §7 "hard parts"), and staged in shared memory;
-//                 main phase  (lane = omega tile): each thread sweeps its tile with a three-term
+//                 main phase  (lane = omega tile; a tile is the INTERLEAVED node set {m, m+T, m+2T, ...}
+//                     of its chunk, T = tiles per chunk, so that a Nyquist cut-off [0, j*) spreads
+//                     evenly over the lanes): each thread sweeps its tile with a three-term
 //                     phasor recurrence v[k+1] = 2cos(d)*v[k] - v[k-1] (cos and sin parts live in
 //                     different lanes) and accumulates A*v into registers: 8 FP64 issue slots per
 //                     (particle,step,node) update instead of ~30 with a per-node sincos.
@@ -374,6 +376,15 @@ SRB_HD void pass_range(const Params& P, const Geom& g, double tau, double tauPre
   const uint32_t jLarge = P.descending ? g.cLo : g.cHi - 1;
   if (pass(jLarge)) { lo = 0; hi = n; return; }
   if (!pass(jSmall)) { lo = 0; hi = 0; return; }
+  if (C::KIND == KIND_RECUR) {
+    // uniform ascending grid: estimate the boundary from pi/|dtau|, then settle it with the exact
+    // predicate (a couple of evaluations instead of a full bisection)
+    const double je = (3.14159265358979323846 / fabs(ssub(tau, tauPrev)) - (double)om[g.cLo]) / P.domega;
+    uint32_t b = (uint32_t)fmin(fmax(ceil(je), 1.0), (double)(n - 1));
+    while (b > 1 && !pass(g.cLo + b - 1)) b--;
+    while (b < n - 1 && pass(g.cLo + b)) b++;
+    lo = 0; hi = b; return;
+  }
   // invariant: pass(a) true, pass(b) false, a and b chunk-relative positions ordered by omega
   uint32_t a = 0, b = n - 1;            // positions in ascending-omega order
   while (b - a > 1) {
@@ -384,9 +395,10 @@ SRB_HD void pass_range(const Params& P, const Geom& g, double tau, double tauPre
   if (P.descending) { lo = n - b; hi = n; } else { lo = 0; hi = b; }
 }
 
-// Phasor seeds for the 16 omega tiles of a chunk (uniform grid): X_m = exp(i(phi0 + m*TW*d)),
-// generated with the three-term recurrence in m.  phi0 is the reference's own rounded phase at
-// the chunk's first node.  The main phase derives the tile's second node as X_m * exp(i*d).
+// Phasor seeds for the 16 interleaved omega tiles of a chunk (uniform grid): tile m starts at chunk
+// node m, X_m = exp(i(phi0 + m*d)), generated with the three-term recurrence in m; consecutive nodes
+// of a tile are 16 grid steps apart, so the main phase advances with exp(i*16*d) (out[] = 2cos(16d),
+// cos(16d), sin(16d)).  phi0 is the reference's own rounded phase at the chunk's first node.
 template <class C>
 SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& sm, int s, double out[3]) {
   using TI = typename C::TI; using TM = typename C::TM;
@@ -394,13 +406,13 @@ SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& 
   double s0, c0, sd, cd;
   sincos_big(smul(w0, tau), &s0, &c0);
   sincos_big(P.domega * tau, &sd, &cd);
-  out[0] = 2.0 * cd; out[1] = cd; out[2] = sd;
   double cw = cd, sw = sd;
 #pragma unroll
-  for (int i = 1; i < C::TW; i <<= 1) { const double t = cw * cw - sw * sw; sw = 2.0 * cw * sw; cw = t; }
+  for (int i = 1; i < 16; i <<= 1) { const double t = cw * cw - sw * sw; sw = 2.0 * cw * sw; cw = t; }
+  out[0] = 2.0 * cw; out[1] = cw; out[2] = sw;
   double xr0 = c0, xi0 = s0;
-  double xr1 = c0 * cw - s0 * sw, xi1 = c0 * sw + s0 * cw;
-  const double cf = 2.0 * cw;
+  double xr1 = c0 * cd - s0 * sd, xi1 = c0 * sd + s0 * cd;
+  const double cf = 2.0 * cd;
   sm.seeds[0][s] = (TM)xr0;  sm.seeds[16][s] = (TM)xi0;
   sm.seeds[1][s] = (TM)xr1;  sm.seeds[17][s] = (TM)xi1;
 #pragma unroll
@@ -458,7 +470,10 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
 }
 
 // -------------------------------------------------------------------------------- main phase
-// one full step of one tile: v0 = seedX, v1 = seedY, then the three-term recurrence
+// smallest tile-local index k with m + T*k >= j (chunk-relative node bound j >= 0): ceil((j-m)/T)
+SRB_HD int tile_lo(int j, int m, int T) { const int d = j - m; return d <= 0 ? 0 : (d + T - 1) / T; }
+
+// one full step of one tile: v0, v1 = first two nodes of the tile, then the three-term recurrence
 template <class C>
 SRB_HD void tile_step_full(const typename C::TM* V, typename C::TM coef, typename C::TM vm, typename C::TM v,
                            ThreadState<C>& st) {
@@ -517,12 +532,13 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
     const TM coef = sm.rec[s][NV];
     if (flag == 3) {   // direct evaluation of this step (phase too large for the recurrence)
-      const int lo = (int)(r & 0x3ffu) - m * TW, hi = (int)((r >> 10) & 0x3ffu) - m * TW;
+      // tile-local k passes iff lo <= m + 16k < hi
+      const int lo = tile_lo((int)(r & 0x3ffu), m, 16), hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
       if (hi <= 0 || lo >= TW) continue;
-      const uint32_t j0 = g.cLo + (uint32_t)(m * TW);
+      const uint32_t j0 = g.cLo + (uint32_t)m;
       for (int k = (lo > 0 ? lo : 0); k < (hi < TW ? hi : TW); k++) {
         TM sn, cs;
-        sincos_t(tmul((TM)((const TI*)P.omega)[j0 + k], coef), &sn, &cs);   // coef slot holds tau
+        sincos_t(tmul((TM)((const TI*)P.omega)[j0 + 16 * k], coef), &sn, &cs);   // coef slot holds tau
         const TM cur = (lane >> 4) ? sn : cs;
 #pragma unroll
         for (int kk = 0; kk < TW; kk++)
@@ -538,7 +554,7 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     if (flag == 1) {
       tile_step_full<C>(V, coef, vm, v, st);
     } else {
-      const int lo = (int)(r & 0x3ffu) - m * TW, hi = (int)((r >> 10) & 0x3ffu) - m * TW;
+      const int lo = tile_lo((int)(r & 0x3ffu), m, 16), hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
       if (hi <= 0 || lo >= TW) continue;
 #pragma unroll
       for (int k = 0; k < TW; k++) {
@@ -598,7 +614,7 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
   for (int s = 0; s < cnt; s++) {
     if (!((anyMask >> s) & 1u)) continue;
     const uint32_t r = sm.rng[s];
-    const int lo = (int)(r & 0x3ffu) - lane * TW, hi = (int)((r >> 10) & 0x3ffu) - lane * TW;
+    const int lo = tile_lo((int)(r & 0x3ffu), lane, 32), hi = tile_lo((int)((r >> 10) & 0x3ffu), lane, 32);
     if (hi <= 0 || lo >= TW) continue;
     TM V[NV];
 #pragma unroll
@@ -644,7 +660,7 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
   const int part = (C::KIND == KIND_RECUR) ? (lane >> 4) : 0;
 #pragma unroll
   for (int k = 0; k < TW; k++) {
-    const uint32_t j = g.cLo + (uint32_t)(tile * TW + k);
+    const uint32_t j = g.cLo + (uint32_t)(tile + C::TILES * k);
     const bool valid = j < g.cHi;
     const size_t idx = (size_t)j + (size_t)P.nOmega * (g.iA2 + (size_t)P.nA2 * g.iPhi) + nTotal * iSnap;
     double re[3], im[3];
@@ -758,7 +774,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
     if (C::KIND == KIND_DIRECT) {
 #pragma unroll
       for (int k = 0; k < C::TW; k++) {
-        const uint32_t j = g.cLo + (uint32_t)(lane * C::TW + k);
+        const uint32_t j = g.cLo + (uint32_t)(lane + 32 * k);
         SRB_ST.wl[k] = j < g.cHi ? (TM)((const TI*)P.omega)[j] : (TM)0;
       }
     }

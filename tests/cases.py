@@ -127,3 +127,53 @@ def c5_args(grid=(256, 32, 32), dtype='double'):
     w1 = 2 * g ** 2 / (1 + K ** 2 / 2)
     return {"grid": [(0.02 * w1, 1.5 * w1), (0, 3 * K / g), (0.0, 2 * np.pi), tuple(grid)],
             "dtype": dtype, "ctx": [0, 0]}
+
+
+def betatron_tracks(Np=1000, seed=0, Num_osc=4, K0=20.0, energy_MeV=500.0, n_p=8e24, energy_spread=0.1,
+                    samples_per_osc=64, substeps=16):
+    """C3: matched Gaussian beam performing betatron oscillations in an ion channel, SI
+    units, parameters of tutorials/Betatron_Example.ipynb (cells 3-4); tracks from a deterministic
+    vectorised leap-frog (momenta at t_k, coordinates staggered by dt/2, as the notebook does).
+    Returns (tracks, c*dt, info)."""
+    from scipy.constants import c, e, m_e, physical_constants
+    r_e = physical_constants['classical electron radius'][0]
+    rs = np.random.RandomState(seed)
+    g0 = energy_MeV * 1e6 * e / (m_e * c ** 2)
+    pz0 = (g0 ** 2 - 1) ** 0.5
+    g0m = (1 + pz0 ** 2 + K0 ** 2) ** 0.5
+    w_p = c * (4 * np.pi * r_e * n_p) ** 0.5
+    w_ch = w_p / (2 * g0m) ** 0.5
+    lam_ch = 2 * np.pi * c / w_ch
+    w_crit = 1.5 * K0 * g0 ** 2 * w_ch
+    T_fin = Num_osc * lam_ch / c
+    Nt = int(Num_osc * samples_per_osc)
+    dt = T_fin / (Nt - 1)
+    R_match = K0 * c / w_p * (2 / g0) ** 0.5
+    x = R_match / 2 ** .5 * rs.randn(Np); y = R_match / 2 ** .5 * rs.randn(Np); z = 1e-6 * rs.randn(Np)
+    ux = K0 / 2 ** .5 * rs.randn(Np); uy = K0 / 2 ** .5 * rs.randn(Np)
+    uz = pz0 * (1 + energy_spread * rs.randn(Np))
+    X = np.empty((6, Np, Nt))
+    h = dt / substeps
+    k = 0.5 * w_p ** 2 / c
+    # momenta live at integer times, coordinates at half-integer times (kick-drift leap-frog)
+    gam = np.sqrt(1 + ux ** 2 + uy ** 2 + uz ** 2)
+    xs, ys, zs = x + 0.5 * h * c * ux / gam, y + 0.5 * h * c * uy / gam, z + 0.5 * h * c * uz / gam
+    for it in range(Nt):
+        X[3, :, it], X[4, :, it], X[5, :, it] = ux, uy, uz
+        for s in range(substeps):
+            if s == substeps // 2:
+                X[0, :, it], X[1, :, it], X[2, :, it] = (xs - 0.5 * h * c * ux / gam, ys - 0.5 * h * c * uy / gam,
+                                                       zs - 0.5 * h * c * uz / gam)
+            ux = ux - h * k * xs; uy = uy - h * k * ys
+            gam = np.sqrt(1 + ux ** 2 + uy ** 2 + uz ** 2)
+            xs = xs + h * c * ux / gam; ys = ys + h * c * uy / gam; zs = zs + h * c * uz / gam
+    tracks = [[X[0, i].copy(), X[1, i].copy(), X[2, i].copy(), X[3, i].copy(), X[4, i].copy(), X[5, i].copy(), 1.0, 0]
+              for i in range(Np)]
+    info = dict(K0=K0, gamma0=g0, omega_crit_1m=w_crit / (2 * np.pi * c))
+    return tracks, c * dt, info
+
+
+def betatron_args(info, grid=(256, 32, 32), dtype='double'):
+    wc = info['omega_crit_1m']
+    return {"grid": [(1e-3 * wc, wc), (0, 2 * info['K0'] / info['gamma0']), (0.0, 2 * np.pi), tuple(grid)],
+            "dtype": dtype, "ctx": [0, 0]}

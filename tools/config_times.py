@@ -29,5 +29,7 @@ trn, dtn, infon = cases.undulator_tracks(24, near=True, seed=0)
 run('C2 near undulator 24 e- (128,256,32) double', cases.undulator_args(infon, near=True), trn, dtn, L_screen=1e5)
 trw, dtw, infow = cases.wiggler_tracks(1000, 256, seed=0)
 run('C3-like betatron 1e3 x 256 (256,32,32) cartesian double', cases.wiggler_args(infow, grid=(256, 32, 32)), trw, dtw, comp='cartesian')
+trb, dtb, infob = cases.betatron_tracks(1000, seed=0)
+run('C3 betatron recipe (SI) 1e3 x 256 (256,32,32) cartesian double', cases.betatron_args(infob), trb, dtb, comp='cartesian')
 trs, dts, infos = cases.wiggler_tracks(10000, 192, seed=0, K0=4.0, gamma0=200.0)
 run('C4-like spiral 1e4 x 192 (512,64,64) float', cases.wiggler_args(infos, grid=(512, 64, 64), dtype='float'), trs, dts)
