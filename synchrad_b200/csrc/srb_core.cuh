@@ -531,21 +531,21 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
 #pragma unroll
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
     const TM coef = sm.rec[s][NV];
+    // tile-local k passes iff lo <= m + 16k < hi ; kmax = largest count over the tiles (tile 0), uniform
+    const int lo = tile_lo((int)(r & 0x3ffu), m, 16), hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
+    const int kmax = tile_lo((int)((r >> 10) & 0x3ffu), 0, 16);
     if (flag == 3) {   // direct evaluation of this step (phase too large for the recurrence)
-      // tile-local k passes iff lo <= m + 16k < hi
-      const int lo = tile_lo((int)(r & 0x3ffu), m, 16), hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
-      if (hi <= 0 || lo >= TW) continue;
       const uint32_t j0 = g.cLo + (uint32_t)m;
-      for (int k = (lo > 0 ? lo : 0); k < (hi < TW ? hi : TW); k++) {
-        TM sn, cs;
-        sincos_t(tmul((TM)((const TI*)P.omega)[j0 + 16 * k], coef), &sn, &cs);   // coef slot holds tau
-        const TM cur = (lane >> 4) ? sn : cs;
 #pragma unroll
-        for (int kk = 0; kk < TW; kk++)
-          if (kk == k) {
+      for (int k = 0; k < TW; k++) {
+        if (k >= kmax) break;                      // warp-uniform
+        if (k >= lo && k < hi) {
+          TM sn, cs;
+          sincos_t(tmul((TM)((const TI*)P.omega)[j0 + 16 * k], coef), &sn, &cs);   // coef slot holds tau
+          const TM cur = (lane >> 4) ? sn : cs;
 #pragma unroll
-            for (int c = 0; c < NV; c++) st.acc[kk * NV + c] = fma(V[c], cur, st.acc[kk * NV + c]);
-          }
+          for (int c = 0; c < NV; c++) st.acc[k * NV + c] = fma(V[c], cur, st.acc[k * NV + c]);
+        }
       }
       continue;
     }
@@ -554,10 +554,9 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     if (flag == 1) {
       tile_step_full<C>(V, coef, vm, v, st);
     } else {
-      const int lo = tile_lo((int)(r & 0x3ffu), m, 16), hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
-      if (hi <= 0 || lo >= TW) continue;
 #pragma unroll
       for (int k = 0; k < TW; k++) {
+        if (k >= kmax) break;                      // warp-uniform: no tile has a passing node beyond
         TM cur;
         if (k == 0) cur = vm; else if (k == 1) cur = v;
         else { const TM vn = fma(coef, v, -vm); vm = v; v = vn; cur = vn; }
@@ -620,9 +619,13 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
 #pragma unroll
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
     const TM tau = sm.rec[s][NV];
+    const int kmin = tile_lo((int)(r & 0x3ffu), 31, 32), kmax = tile_lo((int)((r >> 10) & 0x3ffu), 0, 32);   // warp-uniform
 #pragma unroll
-    for (int k = 0; k < TW; k++)
+    for (int k = 0; k < TW; k++) {
+      if (k >= kmax) break;
+      if (k < kmin) continue;
       if (k >= lo && k < hi) direct_update<C>(V, st.wl[k], tau, k, st);
+    }
   }
 }
 
