@@ -125,7 +125,18 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
                    for _ in range(n_out)]
         sp = (ctypes.c_void_p * n_out)(*[s.data_ptr() for s in spectra])
         nbytes = lib.srb_scratch_bytes(ctypes.byref(g), ctypes.byref(t)) if n_tracks else 0
-        scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev) if nbytes else None
+        scratch = None
+        if nbytes:
+            # scratch = [pre-pass planes][private partial spectra]; a smaller buffer is legal and only
+            # reduces parallelism / disables the pre-pass, so back off instead of failing on a full GPU
+            for frac in (1.0, 0.25, 0.0):
+                try:
+                    n_try = int(nbytes * frac)
+                    scratch = torch.empty(n_try, dtype=torch.uint8, device=dev) if n_try else None
+                    nbytes = n_try
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
         cnt = torch.zeros(2, dtype=torch.int64, device=dev) if counters else None
         if timing:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -317,3 +317,21 @@ def test_file_tracks_to_file_spectrum(cuda_lib, oracle, tmp_path):
     calc.calculate_spectrum(file_tracks=ftr, verbose=False)
     ref2 = oracle.calculate_spectrum(args, tracks, dt)
     assert_close(calc, ref2['radiation'])
+
+
+# ---------------------------------------------------------------------------- differential fuzz
+@pytest.mark.parametrize('seed', [10, 11, 12])
+def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
+    import contextlib
+    import io
+    import fuzzcases
+    rs = np.random.RandomState(seed)
+    for i in range(25):
+        A, tracks, dt, kw = fuzzcases.rand_case(rs)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = oracle.calculate_spectrum(A, tracks, dt, **kw)
+            phasors = ('auto',) if A.get('Features') else ('auto', 'direct')
+            for phasor in phasors:
+                calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
+                e = fuzzcases.vector_errors(calc.Data['radiation'], ref['radiation'])
+                assert e < 1e-9, (seed, i, phasor, e, A['grid'], A.get('mode'), A.get('Features'), kw)
