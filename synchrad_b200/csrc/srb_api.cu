@@ -43,7 +43,8 @@ constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 // resident blocks per SM the register budget is tuned for: accumulators must stay in registers
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
-  return C::KIND == srb::KIND_DIRECT ? SRB_MINB_DIRECT : (accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB));
+  if (C::KIND == srb::KIND_DIRECT) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
+  return accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB);
 }
 
 template <class C>
