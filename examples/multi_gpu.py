@@ -15,10 +15,8 @@ sys.path.insert(0, ROOT)
 from synchrad.calc import SynchRad             # noqa: E402
 from synchrad_b200 import synthetic           # noqa: E402
 
-local = int(os.environ.get('LOCAL_RANK', 0))
-torch.cuda.set_device(local)
-if int(os.environ.get('WORLD_SIZE', 1)) > 1:
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+# no explicit setup: with 'ctx': 'mpi' SynchRad joins the torchrun job itself (one NCCL group, one rank per
+# GPU), the way the reference picks up MPI.COMM_WORLD
 tracks = synthetic.batch_to_track_list(synthetic.c5_batch(64, 2000, seed=7))   # same list on every rank
 args = synthetic.c5_args((256, 32, 32))
 args['ctx'] = 'mpi'

@@ -25,15 +25,27 @@ from . import host
 from .utils import Utilities
 
 
-def _dist():
-    """torch.distributed, if a process group is up (the MPI.COMM_WORLD of calc.py:86-92)."""
+def _dist(auto_init=False):
+    """torch.distributed, if a process group is up (the MPI.COMM_WORLD of calc.py:86-92).
+
+    The reference picks up MPI implicitly when launched under mpirun; the equivalent here is a
+    torchrun launch (RANK / WORLD_SIZE / MASTER_* in the environment): with `ctx='mpi'` and no
+    process group yet, one NCCL group is created, one rank per GPU (LOCAL_RANK)."""
     try:
         import torch.distributed as dist
     except ImportError:          # pragma: no cover
         return None
-    if dist.is_available() and dist.is_initialized():
-        return dist
-    return None
+    if not dist.is_available():
+        return None
+    if not dist.is_initialized() and auto_init and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:                    # host-only use (analysis objects, CPU tests)
+            dist.init_process_group('gloo')
+    return dist if dist.is_initialized() else None
 
 
 class SynchRad(Utilities):
@@ -41,7 +53,7 @@ class SynchRad(Utilities):
     (calc.py:30-84, :108-167) for the meaning of `Args` and of the keyword arguments."""
 
     def __init__(self, Args={}, file_spectrum=None):
-        dist = _dist()
+        dist = _dist(auto_init=isinstance(Args, dict) and Args.get('ctx') == 'mpi')
         if dist is not None:
             self.comm = dist
             self.rank = dist.get_rank()
