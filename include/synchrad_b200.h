@@ -50,6 +50,12 @@ extern "C" {
  *      cosines alone; it has no reproducible answer to be bit-compatible with.) */
 #define SRB_DTYPE_F64 0
 #define SRB_DTYPE_F32 1
+/* F32_LITERAL: every operation of the reference kernels in fp32, in the reference's order, per-node
+ *      Nyquist guard on fp32 phases (srb_literal.cuh).  Arrays are still float64 buffers; tracks are
+ *      rounded to fp32 on load (the reference's astype(float32)); tables must hold fp32-representable
+ *      values computed as `_init_data` computes them in float32.  Reproduces the reference's single-
+ *      precision behaviour, including its ~0.4 rad phase noise. */
+#define SRB_DTYPE_F32_LITERAL 2
 
 /* phasor: how exp(i*omega*tau) is evaluated per node */
 #define SRB_PHASOR_AUTO 0   /* recurrence when omega_uniform, else direct */
@@ -133,7 +139,7 @@ int srb_swap_axes(const double* src, double* dst, uint32_t nSnaps, uint32_t nOme
 
 /* How the last srb_integrate was configured (for benchmarks/diagnostics). */
 typedef struct srb_launch_info {
-  int32_t kind;        /* 0 direct, 1 recurrence */
+  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32 */
   int32_t tile_width;  /* omega nodes per thread */
   uint32_t chunk_nodes, n_chunks, n_virtual_dirs, n_particle_chunks;
   uint32_t grid_blocks, block_threads, smem_bytes;

@@ -15,7 +15,9 @@ tests/test_undulator_analytic.py:98-100).  What changed underneath:
 Documented deviations: string options are compared with `==` (the reference
 uses `is`); `dtype='single'` is accepted as an alias of `'float'`; `ctx=None` selects the
 current CUDA device instead of prompting on stdin; `native` is honoured only when truthy and
-dtype is float (Q9); the cross-particle sum is carried in fp64 (Q5).
+dtype is float (Q9); the cross-particle sum is carried in fp64 (Q5); `dtype='float'` is mixed precision
+by default (see host.grid_tables), `Args['float_mode']='literal'` selects the all-fp32 reproduction of
+the reference's single-precision kernels.
 """
 import os
 
@@ -130,7 +132,8 @@ class SynchRad(Utilities):
             return
         from . import _lib
         _lib.load()
-        self._native = bool(self.Args.get('native', False)) and self.dtype is np.single
+        self._native = bool(self.Args.get('native', False)) and self.dtype is np.single \
+            and host.float_mode(self.Args) == 'mixed'
         self._phasor = self.Args.get('phasor', 'auto')    # extension: 'auto' | 'direct' | 'recur'
 
     def _set_snap_iterations(self, it_range, nSnaps):
@@ -230,7 +233,7 @@ class SynchRad(Utilities):
         self.last_run = {
             'passed_updates': int(c[0]), 'visited_updates': int(c[1]),
             'updates': int(packed.updates_per_node) * int(self.Args['numGridNodes']),
-            'kernel': 'recurrence' if res.info.kind == 1 else 'direct', 'integrate_ms': res.elapsed_ms,
+            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal'}[int(res.info.kind)], 'integrate_ms': res.elapsed_ms,
             'tile_width': int(res.info.tile_width), 'particle_chunks': int(res.info.n_particle_chunks),
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
             'h2d_bytes': int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/synchrad_b200.h"
-#include "srb_core.cuh"
+#include "srb_literal.cuh"
 
 namespace {
 
@@ -43,7 +43,7 @@ constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 // resident blocks per SM the register budget is tuned for: accumulators must stay in registers
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
-  if (C::KIND == srb::KIND_DIRECT) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
+  if (C::KIND != srb::KIND_RECUR) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
   return accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB);
 }
 
@@ -138,7 +138,7 @@ template <class C> Launcher make_launcher() {
   return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK};
 }
 
-using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::MODE_FAR; using srb::MODE_NEAR;
+using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::MODE_FAR; using srb::MODE_NEAR;
 
 // kind, mode, dtype, native, tile width, far components -> kernel
 bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* L) {
@@ -159,6 +159,11 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, 3, float)
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, 3, float) SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, 3, float)
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, 3, float)
+  // literal fp32 (dtype 2)
+  SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 4, 3, float)
+  SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 2, 3, float)
+  SRB_CASE(KIND_LITERAL, MODE_NEAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_NEAR, 2, false, 4, 3, float)
+  SRB_CASE(KIND_LITERAL, MODE_NEAR, 2, false, 2, 3, float)
 #undef SRB_BOTH
 #undef SRB_CASE
   return false;
@@ -180,7 +185,7 @@ int validate(const srb_grid* g, const srb_tracks* t) {
   if (g->mode != SRB_MODE_FAR && g->mode != SRB_MODE_NEAR) return fail("bad mode");
   if (srb_num_spectra(g->mode, g->comp) < 0)
     return fail("no such kernel: comp/mode combination does not exist in the reference");
-  if (g->dtype != SRB_DTYPE_F64 && g->dtype != SRB_DTYPE_F32) return fail("bad dtype");
+  if (g->dtype != SRB_DTYPE_F64 && g->dtype != SRB_DTYPE_F32 && g->dtype != SRB_DTYPE_F32_LITERAL) return fail("bad dtype");
   if (g->nOmega == 0 || g->nAxis2 == 0 || g->nPhi == 0) return fail("empty grid");
   if (g->nSnaps == 0) return fail("nSnaps must be >= 1");
   if ((uint64_t)g->nOmega * g->nAxis2 * g->nPhi >= (1ull << 32)) return fail("grid too large (uint32 node index, as in the reference)");
@@ -207,8 +212,10 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (g->phasor == SRB_PHASOR_AUTO && g->mode == SRB_MODE_NEAR && g->dtype == SRB_DTYPE_F64 &&
       std::fabs(g->omega_last_host * g->L_screen) > 262144.0)
     p->kind = KIND_DIRECT;
+  if (g->dtype == SRB_DTYPE_F32_LITERAL) p->kind = KIND_LITERAL;
   p->native = (p->kind == KIND_DIRECT && g->dtype == SRB_DTYPE_F32 && g->native != 0);   // Q9
   const int tiles = p->kind == KIND_RECUR ? 16 : 32;
+  if (p->kind == KIND_LITERAL && g->phasor == SRB_PHASOR_RECUR) return fail("the literal fp32 kernels have no recurrence variant");
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
@@ -235,7 +242,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   const uint64_t slots = (uint64_t)p->numSM * p->blocksPerSM;
   uint64_t maxPC = t->nTracks ? t->nTracks : 1;
   // scratch = [pre-pass planes][private partial spectra]; the pre-pass is used when it fits
-  p->preDoubles = (size_t)(g->mode == SRB_MODE_FAR ? 6 : 3) * t->totalSteps_host;
+  p->preDoubles = p->kind == KIND_LITERAL ? 0 : (size_t)(g->mode == SRB_MODE_FAR ? 6 : 3) * t->totalSteps_host;
   if (!unlimited) {
     if (scratch_bytes >= p->preDoubles * 8) scratch_bytes -= p->preDoubles * 8;
     else p->preDoubles = 0;

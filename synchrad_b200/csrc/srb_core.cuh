@@ -53,7 +53,7 @@ namespace srb {
 
 enum { MODE_FAR = 0, MODE_NEAR = 1 };
 enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
-enum { KIND_DIRECT = 0, KIND_RECUR = 1 };
+enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2 };   // LITERAL: srb_literal.cuh
 constexpr int SUB = 32;  // steps per sub-batch (= lanes of the prep phase)
 
 // ---- strict (uncontracted, round-to-nearest) double arithmetic: the oracle's operation order
@@ -233,10 +233,11 @@ struct Cfg {
   static constexpr int NV = (MODE_ == MODE_FAR) ? NC_ : 6;        // per-step vector entries in `rec`
   // accumulators per node: split layout (recurrence) holds one part (cos or sin) of NV sums,
   // the direct layout holds Re and Im of the 3 (far: NC) amplitude components
-  static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV : ((MODE_ == MODE_FAR) ? 2 * NC_ : 6);
+  static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV : ((MODE_ == MODE_FAR && KIND_ == KIND_DIRECT) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
-  static constexpr int NREC = ((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1;
+  static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
+                                                     : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
   static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : 1;
 };
 
@@ -250,7 +251,9 @@ struct WarpSmem {
 template <class C>
 struct ThreadState {
   typename C::TM acc[C::NACC];
-  typename C::TM wl[C::KIND == KIND_DIRECT ? C::TW : 1];   // direct kind: this lane's omega nodes
+  typename C::TM wl[C::KIND != KIND_RECUR ? C::TW : 1];    // direct / literal kinds: this lane's omega nodes
+  typename C::TM pprev[C::KIND == KIND_LITERAL ? C::TW : 1];   // literal kind: per-node phasePrev
+  typename C::TM ff[C::KIND == KIND_LITERAL ? C::TW : 1];      // literal kind: per-node FormFactor
   unsigned long long nPass, nAll;
 };
 
@@ -730,6 +733,11 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
   }
 }
 
+// literal fp32 kind (srb_literal.cuh), used by warp_task below
+template <class C> SRB_HD void lit_prep_phase(const Params&, const Geom&, const TrackView&, uint32_t, int, int, WarpSmem<C>&);
+template <class C> SRB_HD void lit_main_phase(const Params&, const Geom&, const WarpSmem<C>&, int, int, ThreadState<C>&);
+template <class C> SRB_HD void lit_flush_lane(const Params&, const Geom&, const TrackView&, uint32_t, uint32_t, int, const ThreadState<C>&);
+
 // -------------------------------------------------------------------------------- warp task
 // One warp integrates all tracks of particle chunk `pc` for virtual direction `vd`.
 template <class C>
@@ -743,7 +751,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
     const double sP = ldv<TI>(P.sinPhi, g.iPhi), cP = ldv<TI>(P.cosPhi, g.iPhi);
     if (C::MODE == MODE_FAR) {
       const double sT = ldv<TI>(P.axA, g.iA2), cT = ldv<TI>(P.axB, g.iA2);
-      if (sizeof(TI) == 8) { g.nx = smul(sT, cP); g.ny = smul(sT, sP); g.nz = cT; g.tx = smul(cT, cP); g.ty = smul(cT, sP); }
+      if (C::KIND != KIND_LITERAL) { g.nx = smul(sT, cP); g.ny = smul(sT, sP); g.nz = cT; g.tx = smul(cT, cP); g.ty = smul(cT, sP); }
       else {  // the reference forms n in fp32 (kernel_farfield.cl:40-42)
         g.nx = (double)((float)sT * (float)cP); g.ny = (double)((float)sT * (float)sP); g.nz = cT;
         g.tx = (double)((float)cT * (float)cP); g.ty = (double)((float)cT * (float)sP);
@@ -751,7 +759,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
       g.tz = -sT; g.px = -sP; g.py = cP; g.pz = 0.0;
     } else {
       const double r = ldv<TI>(P.axA, g.iA2);
-      if (sizeof(TI) == 8) { g.nx = smul(r, cP); g.ny = smul(r, sP); }
+      if (C::KIND != KIND_LITERAL) { g.nx = smul(r, cP); g.ny = smul(r, sP); }
       else { g.nx = (double)((float)r * (float)cP); g.ny = (double)((float)r * (float)sP); }
       g.nz = P.L;
       g.tx = g.ty = g.tz = g.px = g.py = g.pz = 0.0;
@@ -774,11 +782,13 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
   const double dtInv = sdiv(1.0, P.dt);
   SRB_LANES_BEGIN
     SRB_ST.nPass = 0; SRB_ST.nAll = 0;
-    if (C::KIND == KIND_DIRECT) {
+    if (C::KIND != KIND_RECUR) {
 #pragma unroll
       for (int k = 0; k < C::TW; k++) {
         const uint32_t j = g.cLo + (uint32_t)(lane + 32 * k);
         SRB_ST.wl[k] = j < g.cHi ? (TM)((const TI*)P.omega)[j] : (TM)0;
+        if (C::KIND == KIND_LITERAL)
+          SRB_ST.ff[k] = (j < g.cHi && P.formFactor) ? (TM)((const TI*)P.formFactor)[j] : (TM)1;
       }
     }
   SRB_LANES_END
@@ -796,6 +806,10 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
     SRB_LANES_BEGIN
 #pragma unroll
       for (int k = 0; k < C::NACC; k++) SRB_ST.acc[k] = (TM)0;
+      if (C::KIND == KIND_LITERAL) {
+#pragma unroll
+        for (int k = 0; k < C::TW; k++) SRB_ST.pprev[k] = (TM)0;      // phasePrev starts at 0 (Q1)
+      }
     SRB_LANES_END
     // loop bounds of kernel_farfield.cl:59-63 (uint wrap-around for itEnd==0 / nSteps==0 not reproduced)
     const uint32_t loopEnd = tv.itEnd > 0 ? tv.itEnd - 1 : 0;
@@ -810,6 +824,14 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
       const uint32_t stop = (uint32_t)(itf + 1) < nComp ? (uint32_t)(itf + 1) : nComp;
       for (uint32_t base = cur; base < stop; base += SUB) {
         const int cnt = (int)(stop - base < (uint32_t)SUB ? stop - base : (uint32_t)SUB);
+        if constexpr (C::KIND == KIND_LITERAL) {
+          SRB_LANES_BEGIN
+            lit_prep_phase<C>(P, g, tv, base, cnt, lane, sm);
+          SRB_LANES_END
+          SRB_LANES_BEGIN
+            lit_main_phase<C>(P, g, sm, cnt, lane, SRB_ST);
+          SRB_LANES_END
+        } else {
         uint32_t fullMask = 0u, anyMask = 0u;   // bit s: step s of the sub-batch is all-pass / has any pass
         SRB_LANES_BEGIN
           const uint32_t fl = prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);
@@ -822,12 +844,14 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
 #endif
         SRB_LANES_END
         SRB_LANES_BEGIN
-          if (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
+          if constexpr (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
+        }
       }
       SRB_LANES_BEGIN
-        flush_lane<C>(P, g, tv, pc, iSnap, lane, st);
+        if constexpr (C::KIND == KIND_LITERAL) lit_flush_lane<C>(P, g, tv, pc, iSnap, lane, SRB_ST);
+        else flush_lane<C>(P, g, tv, pc, iSnap, lane, st);
       SRB_LANES_END
       cur = (uint32_t)(itf + 1);
       iSnap++;

@@ -95,8 +95,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
             ff = torch.from_numpy(host.form_factor(Args)).to(dev)
 
         g = _lib.srb_grid()
-        g.mode, g.comp, g.dtype = _lib.MODE[mode], _lib.COMP[comp], _lib.DTYPE[
-            'double' if dtype is np.double else 'float']
+        literal = host.float_mode(Args) == 'literal'
+        g.mode, g.comp = _lib.MODE[mode], _lib.COMP[comp]
+        g.dtype = _lib.DTYPE['double' if dtype is np.double else ('float_literal' if literal else 'float')]
         g.native = 1 if native else 0
         g.phasor = _lib.PHASOR[phasor]
         g.omega_uniform = 1 if grid.uniform else 0
@@ -108,9 +109,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
             g.sinTheta, g.cosTheta = T['sinTheta'].data_ptr(), T['cosTheta'].data_ptr()
         else:
             g.radius = T['radius'].data_ptr()
-            g.L_screen = float(Args['L_screen'])
+            g.L_screen = float(np.float32(Args['L_screen'])) if literal else float(Args['L_screen'])
         g.formFactor = ff.data_ptr() if ff is not None else None
-        g.dt = float(Args['timeStep']) if (timeStep is None or dtype is np.double) else float(timeStep)
+        g.dt = float(Args['timeStep']) if (timeStep is None or dtype is np.double or literal) else float(timeStep)
         g.omega_first_host = float(grid.host['omega'][0])
         g.omega_last_host = float(grid.host['omega'][-1])
 

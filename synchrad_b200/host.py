@@ -108,6 +108,32 @@ def omega_is_uniform(Args):
         int(Args['gridNodeNums'][0]) >= 2 and Args['grid'][0][1] > Args['grid'][0][0]
 
 
+def float_mode(Args):
+    """'mixed' (default) or 'literal' for dtype='float'; always 'double' semantics otherwise.
+    Extension key `Args['float_mode']`, see grid_tables and csrc/srb_literal.cuh."""
+    if np_dtype(Args['dtype']) is np.double:
+        return None
+    mode = Args.get('float_mode', 'mixed')
+    if mode not in ('mixed', 'literal'):
+        raise ValueError(f"float_mode must be 'mixed' or 'literal', got {mode!r}")
+    return mode
+
+
+def literal_tables(Args):
+    """float_mode='literal': exactly the float32 arrays `_init_data` uploads (calc.py:494-512), stored
+    in float64 buffers (every value is float32-representable)."""
+    f = np.float32
+    T = {'omega': f(2 * np.pi) * Args['omega'].astype(f),
+         'sinPhi': np.sin(Args['phi'].astype(f)), 'cosPhi': np.cos(Args['phi'].astype(f))}
+    if Args['mode'] == 'far':
+        T['sinTheta'] = np.sin(Args['theta'].astype(f))
+        T['cosTheta'] = np.cos(Args['theta'].astype(f))
+    else:
+        T['radius'] = Args['radius'].astype(f)
+    assert all(v.dtype == np.float32 for v in T.values())
+    return {k: np.ascontiguousarray(v.astype(np.float64)) for k, v in T.items()}
+
+
 def grid_tables(Args, dtype=None):
     """The float64 arrays the kernels read: omega pre-multiplied by 2*pi (calc.py:494-495),
     sin/cos of the angular axes (calc.py:498-512).
@@ -117,6 +143,8 @@ def grid_tables(Args, dtype=None):
     perturbs the phase by ~0.4 rad on the undulator test (fp32 spectrum 5.7 % of max
     away from fp64), so this implementation keeps tables, tracks and the per-(direction, step)
     work in fp64 and runs only the per-omega phasor/accumulate arithmetic in fp32."""
+    if float_mode(Args) == 'literal':
+        return literal_tables(Args)
     ax = axes64(Args)
     T = {'omega': np.ascontiguousarray(np.double(2 * np.pi) * ax['omega']),
          'sinPhi': np.ascontiguousarray(np.sin(ax['phi'])),
@@ -131,6 +159,10 @@ def grid_tables(Args, dtype=None):
 
 def form_factor(Args, dtype=None):
     """Gaussian particle form factor exp(-(2 pi omega sigma)^2 / 2) (calc.py:475-478), float64."""
+    if float_mode(Args) == 'literal':      # float32 arithmetic as in the reference
+        f = np.float32
+        e = f(-0.5) * (f(2 * np.pi) * Args['omega'].astype(f) * f(Args['sigma_particle'])) ** 2
+        return np.ascontiguousarray(np.exp(e).astype(np.float64))
     om = axes64(Args)['omega']
     e = -0.5 * (2 * np.pi * om * float(Args['sigma_particle'])) ** 2
     return np.ascontiguousarray(np.exp(e))

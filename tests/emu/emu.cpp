@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "../../include/synchrad_b200.h"
-#include "../../synchrad_b200/csrc/srb_core.cuh"
+#include "../../synchrad_b200/csrc/srb_literal.cuh"
 
 using namespace srb;
 
@@ -48,6 +48,7 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   P.L = g->L_screen; P.dt = g->dt;
   P.descending = g->omega_last_host < g->omega_first_host ? 1 : 0;
   P.domega = g->nOmega > 1 ? (g->omega_last_host - g->omega_first_host) / (double)(g->nOmega - 1) : 0.0;
+  if (g->dtype == SRB_DTYPE_F32_LITERAL) kind = KIND_LITERAL;
   const int tiles = kind == KIND_RECUR ? 16 : 32;
   P.chunkNodes = (uint32_t)(tiles * tw);
   P.nChunks = (g->nOmega + P.chunkNodes - 1) / P.chunkNodes;
@@ -84,6 +85,7 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
     P.pre = pre.data(); P.preStride = total;
   }
   const bool f32 = g->dtype == SRB_DTYPE_F32;
+  if (kind == KIND_LITERAL) { P.pre = nullptr; }
   bool ok = false;
   const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
   const int nc = (kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
@@ -99,6 +101,9 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   EMU_CASE(KIND_DIRECT, MODE_NEAR, 8) EMU_CASE(KIND_DIRECT, MODE_NEAR, 4) EMU_CASE(KIND_DIRECT, MODE_NEAR, 2)
 #undef EMU_CASE
 #undef EMU_CASE1
+#define EMU_LIT(M, TWV) if (kind == KIND_LITERAL && g->mode == M && tw == TWV) { run_all<Cfg<double, float, M, KIND_LITERAL, TWV, false, 3>>(P, counters); ok = true; }
+  EMU_LIT(MODE_FAR, 8) EMU_LIT(MODE_FAR, 4) EMU_LIT(MODE_FAR, 2) EMU_LIT(MODE_NEAR, 8) EMU_LIT(MODE_NEAR, 4) EMU_LIT(MODE_NEAR, 2)
+#undef EMU_LIT
   if (!ok) return -1;
   for (uint32_t s = 0; s + 1 < nPC; s++)
     for (int c = 0; c < nOut; c++)

@@ -34,12 +34,14 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
         A['L_screen'] = L_screen
     A['timeStep'] = dtype(timeStep)
     T = host.grid_tables(A)
-    weights = [t[6] for t in tracks]
+    literal_pre = A.get('float_mode') == 'literal' and A.get('dtype', 'double') != 'double'
+    weights = [float(np.float32(t[6])) if literal_pre else t[6] for t in tracks]
     pk = host.pack_tracks(tracks, weights, np.double, it_range, nSnaps)
     n_w, n_2, n_p = (int(v) for v in A['gridNodeNums'])
     g = _lib.srb_grid()
     g.mode, g.comp = _lib.MODE[A['mode']], _lib.COMP[comp]
-    g.dtype = 0 if dtype is np.double else 1
+    literal = host.float_mode(A) == 'literal'
+    g.dtype = 0 if dtype is np.double else (2 if literal else 1)
     g.omega_uniform = 1 if host.omega_is_uniform(A) else 0
     g.nOmega, g.nAxis2, g.nPhi, g.nSnaps = n_w, n_2, n_p, nSnaps
     g.omega = T['omega'].ctypes.data
@@ -48,10 +50,10 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
         g.sinTheta, g.cosTheta = T['sinTheta'].ctypes.data, T['cosTheta'].ctypes.data
     else:
         g.radius = T['radius'].ctypes.data
-        g.L_screen = float(L_screen)
+        g.L_screen = float(np.float32(L_screen)) if literal else float(L_screen)
     ff = host.form_factor(A)
     g.formFactor = ff.ctypes.data
-    g.dt = float(timeStep)
+    g.dt = float(np.float32(timeStep)) if literal else float(timeStep)
     g.omega_first_host, g.omega_last_host = float(T['omega'][0]), float(T['omega'][-1])
     t = _lib.srb_tracks()
     t.nTracks = pk.n
@@ -64,6 +66,8 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
     sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
     kind_i = 1 if kind == 'recur' else 0
+    if literal:
+        kind_i, tw = 0, None   # the C side switches to the literal kind; tile widths of the direct layout
     if tw is None:
         tiles = 16 if kind_i else 32
         opts = ([4, 8, 16] if A['mode'] == 'far' else [2, 4, 8]) if kind_i else [2, 4, 8]

@@ -129,3 +129,22 @@ def test_device_sincos_accuracy():
                        c.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(x.size))
     np.testing.assert_allclose(s, [0, 1, -1, 0, 1e-300], atol=2e-16)
     np.testing.assert_allclose(c, [1, 0, 0, -1, 1], atol=2e-16)
+
+
+@pytest.mark.parametrize('near', [False, True])
+def test_literal_fp32_mode_matches_the_fp32_oracle(oracle, near):
+    """float_mode='literal' (srb_literal.cuh): every operation in fp32 in the reference's order, per-node
+    guard on fp32 phases.  Agreement with the strict fp32 restatement, including IDENTICAL guard
+    decisions (in the near field fp32 phases of 1e10 rad make the guard fail at random)."""
+    tr, dt, info = cases.undulator_tracks(2, seed=3)
+    kw = dict(L_screen=1e5) if near else {}
+    comps = ['total', 'cartesian_complex'] if near else ['total', 'cartesian', 'cartesian_complex', 'spheric_complex']
+    for comp in comps:
+        a32 = cases.undulator_args(info, near=near, grid=(100, 4, 3), dtype='float')
+        lit = oracle.calculate_spectrum(a32, tr, dt, comp=comp, sigma_particle=2e-5, nSnaps=2, **kw)
+        a = dict(a32)
+        a['float_mode'] = 'literal'
+        rad, cnt = emu.run(a, tr, dt, comp=comp, sigma_particle=2e-5, nSnaps=2, nPC=2, **kw)
+        assert cnt[0] == lit['passed'], (comp, cnt, lit['passed'])
+        for k in rad:
+            assert max(rel_errors(rad[k], lit['radiation'][k])) < 1e-6, (comp, k)
