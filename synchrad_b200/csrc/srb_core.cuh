@@ -17,12 +17,15 @@
 //                     of its chunk, T = tiles per chunk, so that a Nyquist cut-off [0, j*) spreads
 //                     evenly over the lanes): each thread sweeps its tile with a three-term
 //                     phasor recurrence v[k+1] = 2cos(d)*v[k] - v[k-1] (cos and sin parts live in
-//                     different lanes) and accumulates A*v into registers: 8 FP64 issue slots per
-//                     (particle,step,node) update instead of ~30 with a per-node sincos.
+//                     different lanes) and accumulates A*v into registers; for total/cartesian only the two
+//                     transverse components of A are carried (A is orthogonal to n): 6 FP64 issue slots
+//                     per (particle,step,node) update instead of ~30 with a per-node sincos.
 //              Non-uniform grids ('wavelengthGrid', 'logGrid', calc.py:390-399) use the DIRECT
 //              main phase (per-node sincos of the same rounded phase the reference forms).
 //              |A|^2*w is added to the spectrum once per (track, snapshot) by the owning thread —
 //              no per-step global traffic, no atomics (deterministic).
+//
+// An all-fp32 reproduction of the reference's single-precision kernels lives in srb_literal.cuh.
 //
 // The file is written so that the same code can be compiled by g++ for a single-warp CPU
 // emulation (tests/emu/, test infrastructure only: it lets the kernel logic be debugged in a

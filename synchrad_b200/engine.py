@@ -60,7 +60,8 @@ class Result:
 
 
 def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='auto',
-              counters=True, device_tracks=None, timing=False, timeStep=None):
+              counters=True, device_tracks=None, timing=False, timeStep=None,
+              max_scratch_bytes=None):
     """Run the hot path for the packed tracks of this rank.
 
     Returns Result with `spectra`: list of float64 device tensors (nSnaps, nPhi, nAxis2, nOmega).
@@ -127,6 +128,8 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
         sp = (ctypes.c_void_p * n_out)(*[s.data_ptr() for s in spectra])
         nbytes = lib.srb_scratch_bytes(ctypes.byref(g), ctypes.byref(t)) if n_tracks else 0
         scratch = None
+        if max_scratch_bytes is not None:
+            nbytes = min(nbytes, int(max_scratch_bytes))
         if nbytes:
             # scratch = [pre-pass planes][private partial spectra]; a smaller buffer is legal and only
             # reduces parallelism / disables the pre-pass, so back off instead of failing on a full GPU

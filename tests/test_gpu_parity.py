@@ -356,3 +356,30 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
                 calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
                 e = fuzzcases.vector_errors(calc.Data['radiation'], ref['radiation'])
                 assert e < 1e-9, (seed, i, phasor, e, A['grid'], A.get('mode'), A.get('Features'), kw)
+
+
+def test_scratch_size_only_changes_parallelism(cuda_lib):
+    """srb_integrate accepts any scratch size: none (one particle chunk, kinematics computed in-kernel),
+    partial, full (pre-pass planes + private partial spectra).  Same spectrum (to summation order)."""
+    import torch
+    from synchrad_b200 import _lib, engine, host
+    tracks, dt = cases.c5_tracks_numpy(30, 300)
+    args, dtype = host.init_args(cases.c5_args(grid=(128, 4, 4)))
+    args['timeStep'] = dt
+    dev = torch.device('cuda', 0)
+    grid = engine.DeviceGrid(args, dtype, dev)
+    pk = host.pack_tracks(tracks, [t[6] for t in tracks], np.double, None, 1)
+    full = engine.integrate(args, dtype, grid, pk, 'total', 1)
+    ref = full.spectra[0].cpu().numpy()
+    assert full.info.n_particle_chunks > 1 and full.info.kernels_launched == 3       # pre-pass, integrate, reduce
+    want = cuda_lib.srb_scratch_bytes  # noqa: F841  (size query is exercised inside engine.integrate)
+    for limit in (0, 3 * ref.nbytes, 6 * 8 * pk.total + 2 * ref.nbytes):
+        res = engine.integrate(args, dtype, grid, pk, 'total', 1, max_scratch_bytes=limit)
+        got = res.spectra[0].cpu().numpy()
+        assert max(rel_errors(got, ref)) < 1e-13, limit
+        if limit == 0:
+            assert res.info.n_particle_chunks == 1 and res.info.kernels_launched == 1
+        elif limit == 3 * ref.nbytes:                    # too small for the pre-pass planes: slabs only
+            assert res.info.n_particle_chunks == 4 and res.info.kernels_launched == 2
+        else:                                            # pre-pass + 2 private spectra
+            assert res.info.n_particle_chunks == 3 and res.info.kernels_launched == 3
