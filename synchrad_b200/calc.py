@@ -197,6 +197,8 @@ class SynchRad(Utilities):
         if it_range is not None:
             self._set_snap_iterations(it_range, nSnaps)
 
+        dt64 = getattr(self, '_timeStep64', float(self.Args['timeStep']))
+        run = dict(native=self._native, phasor=self._phasor, timing=True, timeStep=dt64)
         if isinstance(particleTracks, host.PackedTracks):
             packed = particleTracks
             if weights_normalize is not None or Np_max is not None:
@@ -204,22 +206,40 @@ class SynchRad(Utilities):
             if (packed.snapStride == 0) != (it_range is not None) or packed.itSnaps.shape[-1] != nSnaps:
                 raise ValueError('pre-packed tracks were packed for a different it_range / nSnaps')
             self.total_weight = float(np.sum(packed.w[:packed.n]))
+            batches = [packed]
         else:
             weights = host.normalized_weights([t[6] for t in particleTracks], weights_normalize)
             for t, w in zip(particleTracks, weights):       # the reference mutates the track list
                 if weights_normalize in ('mean', 'max', 'ones') and isinstance(t, list):
                     t[6] = float(w)
             self.total_weight = float(np.sum(weights)) if len(weights) else 0.0
-            alloc = engine.PinnedAlloc()
-            packed = host.pack_tracks(particleTracks, weights, np.double, it_range, nSnaps, alloc)
+            # Track sets larger than the device are integrated batch by batch into the same spectra
+            # (the reference streams one track at a time, calc.py:257-267).  Per sample: 48 B of
+            # coordinates + 48 B of pre-pass planes.
+            lengths = [np.asarray(t[0]).size for t in particleTracks]
+            budget = self.Args.get('max_batch_bytes')
+            if budget is None:
+                free, _ = torch.cuda.mem_get_info(self.device)
+                budget = int(0.6 * free)
+            spans = host.split_batches(lengths, max(int(budget) // 96, 1))
+            batches = spans
+        res, h2d, upd, ms = None, 0, 0, 0.0
+        for b in batches:
+            if isinstance(b, tuple):
+                alloc = engine.PinnedAlloc()
+                packed = host.pack_tracks(particleTracks[b[0]:b[1]], weights[b[0]:b[1]], np.double, it_range,
+                                          nSnaps, alloc)
+            res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
+                                   spectra=None if res is None else res.spectra,
+                                   counters_into=None if res is None else res.counters, **run)
+            h2d += int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes
+                       + packed.itStart.nbytes + packed.itEnd.nbytes + packed.itSnaps.nbytes)
+            upd += int(packed.updates_per_node)
+            ms += res.elapsed_ms
         if it_range is None and packed.n:
             self.snap_iterations = np.array(packed.itSnaps[packed.n - 1])   # last track's, as in the reference
         elif it_range is None:
             self.snap_iterations = np.zeros(nSnaps, dtype=np.uint32)
-
-        res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
-                               native=self._native, phasor=self._phasor, timing=True,
-                               timeStep=getattr(self, '_timeStep64', float(self.Args['timeStep'])))
         n_w, n_2, n_p = (int(v) for v in self.Args['gridNodeNums'])
         dev_out = engine.to_host_layout(res.spectra, nSnaps, n_w, n_2, n_p)
         keys = host.COMP_KEYS[comp]
@@ -232,12 +252,11 @@ class SynchRad(Utilities):
         c = cnt.cpu().numpy()
         self.last_run = {
             'passed_updates': int(c[0]), 'visited_updates': int(c[1]),
-            'updates': int(packed.updates_per_node) * int(self.Args['numGridNodes']),
-            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal'}[int(res.info.kind)], 'integrate_ms': res.elapsed_ms,
+            'updates': upd * int(self.Args['numGridNodes']), 'batches': len(batches),
+            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal'}[int(res.info.kind)], 'integrate_ms': ms,
             'tile_width': int(res.info.tile_width), 'particle_chunks': int(res.info.n_particle_chunks),
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
-            'h2d_bytes': int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes
-                             + packed.itStart.nbytes + packed.itEnd.nbytes + packed.itSnaps.nbytes),
+            'h2d_bytes': h2d,
             'd2h_bytes': int(sum(v.nbytes for v in self.Data['radiation'].values())),
         }
 

@@ -61,10 +61,12 @@ class Result:
 
 def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='auto',
               counters=True, device_tracks=None, timing=False, timeStep=None,
-              max_scratch_bytes=None):
+              max_scratch_bytes=None, spectra=None, counters_into=None):
     """Run the hot path for the packed tracks of this rank.
 
     Returns Result with `spectra`: list of float64 device tensors (nSnaps, nPhi, nAxis2, nOmega).
+    `spectra` (optional): tensors of a previous call to accumulate into (the C ABI is `+=`), which is
+    how track sets larger than the device memory are processed batch by batch.
     `device_tracks` (optional) are tracks already resident on the device: a dict with the
     PackedTracks field names holding torch tensors (used by bench.py's device-resident leg).
     """
@@ -123,8 +125,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
         t.itSnapsStride = stride
         t.totalSteps_host = total
 
-        spectra = [torch.zeros((int(nSnaps), n_p, n_2, n_w), dtype=torch.float64, device=dev)
-                   for _ in range(n_out)]
+        if spectra is None:
+            spectra = [torch.zeros((int(nSnaps), n_p, n_2, n_w), dtype=torch.float64, device=dev)
+                       for _ in range(n_out)]
         sp = (ctypes.c_void_p * n_out)(*[s.data_ptr() for s in spectra])
         nbytes = lib.srb_scratch_bytes(ctypes.byref(g), ctypes.byref(t)) if n_tracks else 0
         scratch = None
@@ -157,6 +160,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
             res.elapsed_ms = e0.elapsed_time(e1)
         info = _lib.srb_launch_info()
         lib.srb_last_launch(ctypes.byref(info))
+        if counters_into is not None and cnt is not None:
+            counters_into += cnt
+            cnt = counters_into
         res.spectra, res.counters, res.info = spectra, cnt, info
         res.updates = None
         # keep inputs alive until the stream has consumed them

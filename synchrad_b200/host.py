@@ -251,3 +251,18 @@ def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
         upd += max(0, min(m - 1, end - 1))
     P.updates_per_node = upd
     return P
+
+
+def split_batches(lengths, max_steps):
+    """Contiguous batches of tracks with at most `max_steps` samples each (a single longer track is
+    its own batch).  Returns a list of (first, last_exclusive) index pairs."""
+    out, start, acc = [], 0, 0
+    for i, n in enumerate(lengths):
+        n = int(n)
+        if i > start and acc + n > max_steps:
+            out.append((start, i))
+            start, acc = i, 0
+        acc += n
+    if start < len(lengths) or not out:
+        out.append((start, len(lengths)))
+    return out

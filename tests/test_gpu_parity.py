@@ -194,6 +194,25 @@ def test_deterministic_and_independent_calls(cuda_lib):
     np.testing.assert_array_equal(a.Data['radiation']['total'], b.Data['radiation']['total'])
 
 
+def test_batched_integration_of_large_track_sets(cuda_lib, oracle):
+    """Track sets larger than the device are integrated batch by batch into the same spectra
+    (Args['max_batch_bytes'] forces small batches here)."""
+    tracks, dt = cases.c5_tracks_numpy(9, 200)
+    tracks = [t[:7] + [s] for t, s in zip(tracks, (0, 4, 0, 9, 2, 0, 0, 7, 1))]
+    args = cases.c5_args(grid=(64, 4, 4))
+    one = run_gpu(args, tracks, dt, comp='cartesian', nSnaps=2, it_range=(0, 220))
+    small = dict(args)
+    small['max_batch_bytes'] = 96 * 450            # two tracks per batch
+    many = run_gpu(small, tracks, dt, comp='cartesian', nSnaps=2, it_range=(0, 220))
+    assert one.last_run['batches'] == 1 and many.last_run['batches'] == 5
+    for k in 'xyz':
+        assert max(rel_errors(many.Data['radiation'][k], one.Data['radiation'][k])) < 1e-13
+    assert many.last_run['passed_updates'] == one.last_run['passed_updates']
+    assert many.last_run['updates'] == one.last_run['updates'] and many.total_weight == one.total_weight
+    ref = oracle.calculate_spectrum(args, tracks, dt, comp='cartesian', nSnaps=2, it_range=(0, 220))
+    assert_close(many, ref['radiation'])
+
+
 def test_full_size_grid_linearity(cuda_lib):
     """At BASELINE's full 256x32x32 grid the oracle is too slow for many particles; use
     size-independent properties: incoherent spectra add over disjoint particle sets, scale

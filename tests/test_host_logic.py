@@ -105,3 +105,11 @@ def test_pack_tracks_empty_and_ragged():
     bad[0][2] = np.zeros(3)
     with pytest.raises(ValueError):
         host.pack_tracks(bad, [1, 1, 1], np.float64, None, 1)
+
+
+def test_split_batches():
+    assert host.split_batches([], 100) == [(0, 0)]
+    assert host.split_batches([10, 10, 10], 100) == [(0, 3)]
+    assert host.split_batches([60, 60, 60], 100) == [(0, 1), (1, 2), (2, 3)]
+    assert host.split_batches([30, 30, 30, 30, 500, 5, 5], 100) == [(0, 3), (3, 4), (4, 5), (5, 7)]
+    assert host.split_batches([500], 100) == [(0, 1)]
