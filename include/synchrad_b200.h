@@ -58,9 +58,11 @@ extern "C" {
 #define SRB_DTYPE_F32_LITERAL 2
 
 /* phasor: how exp(i*omega*tau) is evaluated per node */
-#define SRB_PHASOR_AUTO 0   /* recurrence when omega_uniform, else direct */
+#define SRB_PHASOR_AUTO 0   /* uniform grid: pair kernel (far, non-spheric) or recurrence; else direct */
 #define SRB_PHASOR_DIRECT 1 /* per-node sincos of the reference's rounded phase */
 #define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
+#define SRB_PHASOR_PAIR 3   /* symmetric node pairs about the tile centre, broadcast pair phasors
+                               (uniform grids, far field, total/cartesian/cartesian_complex) */
 
 /* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
  * Tables are float64 arrays with the content `_init_data` uploads (calc.py:486-512): omega is
@@ -139,7 +141,7 @@ int srb_swap_axes(const double* src, double* dst, uint32_t nSnaps, uint32_t nOme
 
 /* How the last srb_integrate was configured (for benchmarks/diagnostics). */
 typedef struct srb_launch_info {
-  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32 */
+  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32, 3 pair */
   int32_t tile_width;  /* omega nodes per thread */
   uint32_t chunk_nodes, n_chunks, n_virtual_dirs, n_particle_chunks;
   uint32_t grid_blocks, block_threads, smem_bytes;

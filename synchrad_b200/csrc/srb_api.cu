@@ -43,7 +43,7 @@ constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 // resident blocks per SM the register budget is tuned for: accumulators must stay in registers
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
-  if (C::KIND != srb::KIND_RECUR) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
+  if (C::KIND == srb::KIND_DIRECT || C::KIND == srb::KIND_LITERAL) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
   return accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB);
 }
 
@@ -138,7 +138,7 @@ template <class C> Launcher make_launcher() {
   return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK};
 }
 
-using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::MODE_FAR; using srb::MODE_NEAR;
+using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::MODE_FAR; using srb::MODE_NEAR;
 
 // kind, mode, dtype, native, tile width, far components -> kernel
 bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* L) {
@@ -159,6 +159,8 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, 3, float)
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 8, 3, float) SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 4, 3, float)
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, 3, float)
+  // symmetric-pair kernel: far field, transverse basis
+  SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 2)
   // literal fp32 (dtype 2)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 4, 3, float)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 2, 3, float)
@@ -205,7 +207,12 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   SRB_CUDA(cudaDeviceGetAttribute(&p->numSM, cudaDevAttrMultiProcessorCount, dev));
   const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
   if (g->phasor == SRB_PHASOR_RECUR && !uniform) return fail("phasor recurrence needs an ascending uniform omega grid");
-  p->kind = (g->phasor == SRB_PHASOR_DIRECT || !uniform) ? KIND_DIRECT : KIND_RECUR;
+  const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
+  const bool pairOk = uniform && g->mode == SRB_MODE_FAR && !spheric;
+  if (g->phasor == SRB_PHASOR_PAIR && !pairOk) return fail("the pair kernel needs a far-field, non-spheric comp on an ascending uniform omega grid");
+  if (g->phasor == SRB_PHASOR_DIRECT || !uniform) p->kind = KIND_DIRECT;
+  else if (g->phasor == SRB_PHASOR_RECUR || !pairOk) p->kind = KIND_RECUR;
+  else p->kind = KIND_PAIR;
   // near field: phase = omega*(t+R) ~ omega*L.  Beyond 2^18 rad the recurrence cannot track the
   // reference's rounded phase to 1e-9 (srb_core.cuh, flag 3), every step would fall back, so the
   // direct kernel (full lane layout) is chosen outright.
@@ -218,6 +225,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (p->kind == KIND_LITERAL && g->phasor == SRB_PHASOR_RECUR) return fail("the literal fp32 kernels have no recurrence variant");
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
+  else if (p->kind == KIND_PAIR) { twMax = 8; twMin = 2; }
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }
@@ -225,8 +233,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
     const int tw = std::atoi(f);
     if (tw >= twMin && tw <= twMax && (tw & (tw - 1)) == 0) p->tw = tw;
   }
-  const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
-  p->nc = (p->kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
+  p->nc = (p->kind == KIND_PAIR || (p->kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric)) ? 2 : 3;
   if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L)) return fail("internal: no kernel for this configuration");
   p->chunkNodes = (uint32_t)p->L.chunk;
   p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;

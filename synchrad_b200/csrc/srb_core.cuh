@@ -56,7 +56,7 @@ namespace srb {
 
 enum { MODE_FAR = 0, MODE_NEAR = 1 };
 enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
-enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2 };   // LITERAL: srb_literal.cuh
+enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh
 constexpr int SUB = 32;  // steps per sub-batch (= lanes of the prep phase)
 
 // ---- strict (uncontracted, round-to-nearest) double arithmetic: the oracle's operation order
@@ -236,12 +236,14 @@ struct Cfg {
   static constexpr int NV = (MODE_ == MODE_FAR) ? NC_ : 6;        // per-step vector entries in `rec`
   // accumulators per node: split layout (recurrence) holds one part (cos or sin) of NV sums,
   // the direct layout holds Re and Im of the 3 (far: NC) amplitude components
-  static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV : ((MODE_ == MODE_FAR && KIND_ == KIND_DIRECT) ? 2 * NC_ : 6);
+  static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV
+      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || KIND_ == KIND_PAIR)) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
+  //          (pair) cos/sin of the TW/2 pair offsets (flag 3: tau in the first of them)
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
-                                                     : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
-  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : 1;
+      : (((NV + (KIND_ == KIND_RECUR ? 3 : (KIND_ == KIND_PAIR ? TW_ : 1))) + 1) & ~1);
+  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : (KIND_ == KIND_PAIR ? 24 : 1);
 };
 
 template <class C>
@@ -254,7 +256,7 @@ struct WarpSmem {
 template <class C>
 struct ThreadState {
   typename C::TM acc[C::NACC];
-  typename C::TM wl[C::KIND != KIND_RECUR ? C::TW : 1];    // direct / literal kinds: this lane's omega nodes
+  typename C::TM wl[(C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) ? C::TW : 1];   // this lane's omega nodes
   typename C::TM pprev[C::KIND == KIND_LITERAL ? C::TW : 1];   // literal kind: per-node phasePrev
   typename C::TM ff[C::KIND == KIND_LITERAL ? C::TW : 1];      // literal kind: per-node FormFactor
   unsigned long long nPass, nAll;
@@ -295,6 +297,15 @@ SRB_HD void near_step_kinematics(const void* ux, const void* uy, const void* uz,
   const double gi = sdiv(1.0, ssqrt(sadd(1.0, sdot3(u0, u1, u2, u0, u1, u2))));
   b[0] = smul(u0, gi); b[1] = smul(u1, gi); b[2] = smul(u2, gi);
 }
+
+// pair kind (srb_pair.cuh)
+template <class C> SRB_HD void make_seeds_pair(const Params&, const Geom&, double, WarpSmem<C>&, int);
+template <class C> SRB_HD void main_pair(const Params&, const Geom&, const WarpSmem<C>&, int, uint32_t, uint32_t, int, ThreadState<C>&);
+template <class C> SRB_HD void pair_node_amp(const ThreadState<C>&, int, double*, double*);
+// literal fp32 kind (srb_literal.cuh), used by warp_task below
+template <class C> SRB_HD void lit_prep_phase(const Params&, const Geom&, const TrackView&, uint32_t, int, int, WarpSmem<C>&);
+template <class C> SRB_HD void lit_main_phase(const Params&, const Geom&, const WarpSmem<C>&, int, int, ThreadState<C>&);
+template <class C> SRB_HD void lit_flush_lane(const Params&, const Geom&, const TrackView&, uint32_t, uint32_t, int, const ThreadState<C>&);
 
 template <class TI> SRB_HD double ldv(const void* p, size_t i) { return (double)((const TI*)p)[i]; }
 
@@ -382,7 +393,7 @@ SRB_HD void pass_range(const Params& P, const Geom& g, double tau, double tauPre
   const uint32_t jLarge = P.descending ? g.cLo : g.cHi - 1;
   if (pass(jLarge)) { lo = 0; hi = n; return; }
   if (!pass(jSmall)) { lo = 0; hi = 0; return; }
-  if (C::KIND == KIND_RECUR) {
+  if (C::KIND == KIND_RECUR || C::KIND == KIND_PAIR) {
     // uniform ascending grid: estimate the boundary from pi/|dtau|, then settle it with the exact
     // predicate (a couple of evaluations instead of a full bisection)
     const double je = (3.14159265358979323846 / fabs(ssub(tau, tauPrev)) - (double)om[g.cLo]) / P.domega;
@@ -458,6 +469,11 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, V);
   else prep_near<C>(P, g, tv, it, r0, r1, r2, rL, V, V + 3);
   double last[3] = {tau, 0.0, 0.0};
+  if constexpr (C::KIND == KIND_PAIR) {
+    const double wl = (double)((const typename C::TI*)P.omega)[g.cHi - 1];
+    if (sizeof(TM) == 8 && fabs(wl * tau) > 262144.0) flag = 3u;
+    else make_seeds_pair<C>(P, g, tau, sm, lane);
+  }
   if (C::KIND == KIND_RECUR) {
     // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
     // beyond |phase| ~ 2^18 that exceeds the 1e-9 parity budget, so such steps are evaluated
@@ -470,7 +486,8 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   st.nPass += hi - lo;
 #pragma unroll
   for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
-  sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau
+  if (C::KIND != KIND_PAIR || flag == 3u)
+    sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau ; pair: flag 3 only
   if (C::KIND == KIND_RECUR) { sm.rec[lane][C::NV + 1] = (TM)last[1]; sm.rec[lane][C::NV + 2] = (TM)last[2]; }
   return flag;
 }
@@ -673,7 +690,9 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
     const bool valid = j < g.cHi;
     const size_t idx = (size_t)j + (size_t)P.nOmega * (g.iA2 + (size_t)P.nA2 * g.iPhi) + nTotal * iSnap;
     double re[3], im[3];
-    if (C::KIND == KIND_DIRECT) {
+    if constexpr (C::KIND == KIND_PAIR) {
+      pair_node_amp<C>(me, k, re, im);
+    } else if constexpr (C::KIND == KIND_DIRECT) {
 #pragma unroll
       for (int c = 0; c < NCF; c++) { re[c] = (double)me.acc[k * NPN + c]; im[c] = (double)me.acc[k * NPN + NCF + c]; }
     } else {
@@ -729,17 +748,12 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
       const double ff = useFF ? (double)((const TI*)P.formFactor)[j] : 1.0;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        if (C::KIND == KIND_DIRECT || part == 0) dest<C>(P, pc, 2 * c)[idx] += wpdt * (re[c] * ff);
-        if (C::KIND == KIND_DIRECT || part == 1) dest<C>(P, pc, 2 * c + 1)[idx] += wpdt * (im[c] * ff);
+        if (C::KIND != KIND_RECUR || part == 0) dest<C>(P, pc, 2 * c)[idx] += wpdt * (re[c] * ff);
+        if (C::KIND != KIND_RECUR || part == 1) dest<C>(P, pc, 2 * c + 1)[idx] += wpdt * (im[c] * ff);
       }
     }
   }
 }
-
-// literal fp32 kind (srb_literal.cuh), used by warp_task below
-template <class C> SRB_HD void lit_prep_phase(const Params&, const Geom&, const TrackView&, uint32_t, int, int, WarpSmem<C>&);
-template <class C> SRB_HD void lit_main_phase(const Params&, const Geom&, const WarpSmem<C>&, int, int, ThreadState<C>&);
-template <class C> SRB_HD void lit_flush_lane(const Params&, const Geom&, const TrackView&, uint32_t, uint32_t, int, const ThreadState<C>&);
 
 // -------------------------------------------------------------------------------- warp task
 // One warp integrates all tracks of particle chunk `pc` for virtual direction `vd`.
@@ -785,7 +799,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
   const double dtInv = sdiv(1.0, P.dt);
   SRB_LANES_BEGIN
     SRB_ST.nPass = 0; SRB_ST.nAll = 0;
-    if (C::KIND != KIND_RECUR) {
+    if (C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) {
 #pragma unroll
       for (int k = 0; k < C::TW; k++) {
         const uint32_t j = g.cLo + (uint32_t)(lane + 32 * k);
@@ -848,6 +862,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
         SRB_LANES_END
         SRB_LANES_BEGIN
           if constexpr (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
+          else if constexpr (C::KIND == KIND_PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
         }

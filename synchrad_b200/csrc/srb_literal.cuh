@@ -14,6 +14,7 @@
 // per (direction, step) in the prep phase, identically to what every node of the reference computes.
 #pragma once
 #include "srb_core.cuh"
+#include "srb_pair.cuh"
 
 namespace srb {
 

@@ -38,7 +38,7 @@ def assert_close(calc, ref_rad, tol=TOL64, what=''):
 
 
 # ---------------------------------------------------------------------------- BASELINE configs
-@pytest.mark.parametrize('phasor', ['auto', 'direct'])
+@pytest.mark.parametrize('phasor', ['auto', 'recur', 'direct'])
 def test_c1_far_undulator_full_grid(cuda_lib, oracle, phasor):
     """configs[0]: tests/test_undulator_analytic.py grid, deterministic single electron."""
     tracks, dt, info = cases.undulator_tracks(1)
@@ -46,7 +46,7 @@ def test_c1_far_undulator_full_grid(cuda_lib, oracle, phasor):
     calc = run_gpu(args, tracks, dt, phasor=phasor)
     ref = oracle.calculate_spectrum(args, tracks, dt)
     assert_close(calc, ref['radiation'], what=phasor)
-    assert calc.last_run['kernel'] == ('recurrence' if phasor == 'auto' else 'direct')
+    assert calc.last_run['kernel'] == {'auto': 'pair', 'recur': 'recurrence', 'direct': 'direct'}[phasor]
     assert calc.last_run['passed_updates'] == ref['passed']            # identical guard decisions
     assert calc.last_run['updates'] == ref['updates'] == 1664 * 131072
     S = calc.Data['radiation']['total'][0]
@@ -119,7 +119,7 @@ def test_c3_like_si_units(cuda_lib, oracle):
 def test_c5_like_small(cuda_lib, oracle):
     tracks, dt = cases.c5_tracks_numpy(6, 1500)
     args = cases.c5_args(grid=(256, 8, 8))
-    for phasor in ('auto', 'direct'):
+    for phasor in ('auto', 'recur', 'direct'):
         calc = run_gpu(args, tracks, dt, phasor=phasor)
         assert_close(calc, oracle.calculate_spectrum(args, tracks, dt)['radiation'], what=phasor)
 
@@ -130,7 +130,7 @@ def test_golden_small_cases(cuda_lib):
     stored = np.load(os.path.join(GOLD, 'small_cases.npz'))
     for name, (args, tracks, dt, kw) in mg.small_cases().items():
         uniform = not args.get('Features')
-        for phasor in (('auto', 'direct') if uniform else ('auto',)):
+        for phasor in (('auto', 'recur', 'direct') if uniform else ('auto',)):
             calc = run_gpu(args, tracks, dt, phasor=phasor, **kw)
             for key in calc.Data['radiation']:
                 e = rel_errors(calc.Data['radiation'][key], stored[f'{name}/{key}'])
@@ -370,7 +370,11 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
         A, tracks, dt, kw = fuzzcases.rand_case(rs)
         with contextlib.redirect_stdout(io.StringIO()):
             ref = oracle.calculate_spectrum(A, tracks, dt, **kw)
-            phasors = ('auto',) if A.get('Features') else ('auto', 'direct')
+            far_plain = A.get('mode', 'far') == 'far' and not kw['comp'].startswith('spheric')
+            if A.get('Features') or A['grid'][-1][0] < 2:
+                phasors = ('auto',)
+            else:
+                phasors = ('auto', 'recur', 'direct') if far_plain else ('auto', 'direct')
             for phasor in phasors:
                 calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
                 e = fuzzcases.vector_errors(calc.Data['radiation'], ref['radiation'])
