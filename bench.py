@@ -260,15 +260,18 @@ def run_product(a):
 
     k_ms = sum(kernel_ms) / len(kernel_ms)
     # DRAM bytes of ONE launch of this exact configuration, from an ncu capture of the same kernel
-    # (profiles/r01_ncu_full_size_launch_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum)
+    # (dram__bytes_read.sum + dram__bytes_write.sum of the full-size launch)
     default_cfg = (a.dtype == 'double' and a.phasor == 'auto' and n_p == 12500 and n_s == 10000)
-    traffic = 26169446912 + 1634786304 if default_cfg else None
+    traffic = 25906307584 + 1754827520 if default_cfg else None   # profiles/r01_ncu_full_size_launch_metrics_pair.csv
     slots_alg = ALG_SLOTS[a.dtype]
     achieved = updates_rank * slots_alg / (k_ms * 1e-3)          # algorithmic slots/s of one launch
     issued = None
+    tw, nc = int(info.tile_width), int(info.n_components)
     if int(info.kind) == 1:      # recurrence: per lane and step (TW-2) chain + NC*TW accumulate + 2 seed ops, for TW half-updates
-        tw, nc = int(info.tile_width), int(info.n_components)
         issued = 2.0 * ((tw - 2) + nc * tw + 2) / tw
+    elif int(info.kind) == 3:    # pair: per lane and step 4 (X = Y*Z) + 2*NC (B = A*X) + 4*NC*TW/2 accumulate, for TW updates
+        issued = (4 + 2 * nc + 2 * nc * tw) / tw
+    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair'}[int(info.kind)]
     roofline = {
         'bound': 'fp64_pipe' if a.dtype == 'double' else 'fp32_pipe',
         'achieved': achieved / 1e12, 'peak': peak.value / 1e12, 'unit': 'Tslot/s (FMA-pipe lane issue slots)',
@@ -279,9 +282,9 @@ def run_product(a):
         'issued_main_loop_slots_per_update': issued,
         'frac_issued_main_loop': (updates_rank * issued / (k_ms * 1e-3) / peak.value) if issued else None,
         'kernel_ms_per_launch': k_ms,
-        'kernel': 'k_integrate<%s, tile %d>' % ('recurrence' if info.kind == 1 else 'direct', info.tile_width),
+        'kernel': 'k_integrate<%s, tile %d>' % (kname, info.tile_width),
         'traffic': traffic,
-        'fp64_pipe_active_ncu': 0.711 if default_cfg else None,   # sm__pipe_fp64_cycles_active, same file
+        'fp64_pipe_active_ncu': 0.664 if default_cfg else None,   # sm__pipe_fp64_cycles_active of the same full-size launch
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }
@@ -295,7 +298,7 @@ def run_product(a):
                         f'{GRID[0]}x{GRID[1]}x{GRID[2]} (omega,theta,phi) far-field, comp=total; '
                         f'N=8 is the whole 10^5-particle C5',
             'grid': list(GRID), 'particles_per_gpu': n_p, 'track_steps': n_s, 'updates_per_step': world * updates_rank,
-            'phasor': 'recurrence' if info.kind == 1 else 'direct', 'tile_width': int(info.tile_width),
+            'phasor': kname, 'tile_width': int(info.tile_width),
             'particle_chunks': int(info.n_particle_chunks), 'grid_blocks': int(info.grid_blocks),
             'l2_policy': f'inputs larger than L2 ({nbytes_tracks / 1e9:.1f} GB of tracks per GPU vs 126 MB)',
             'guard_pass_fraction': guard_pass, 'spectrum_checksum': checksum,
@@ -323,7 +326,7 @@ def main():
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--dtype', default='double', choices=['double', 'float'])
-    p.add_argument('--phasor', default='auto', choices=['auto', 'direct'])
+    p.add_argument('--phasor', default='auto', choices=['auto', 'direct', 'recur', 'pair'])
     p.add_argument('--particles-per-gpu', type=int, default=12500)
     p.add_argument('--track-steps', type=int, default=10000)
     p.add_argument('--e2e-steps', type=int, default=2)
