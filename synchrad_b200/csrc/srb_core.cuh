@@ -25,7 +25,8 @@
 //              |A|^2*w is added to the spectrum once per (track, snapshot) by the owning thread —
 //              no per-step global traffic, no atomics (deterministic).
 //
-// An all-fp32 reproduction of the reference's single-precision kernels lives in srb_literal.cuh.
+// The fastest far-field main phase (symmetric node pairs, no per-lane recurrence) lives in srb_pair.cuh;
+// an all-fp32 reproduction of the reference's single-precision kernels in srb_literal.cuh.
 //
 // The file is written so that the same code can be compiled by g++ for a single-warp CPU
 // emulation (tests/emu/, test infrastructure only: it lets the kernel logic be debugged in a

@@ -12,7 +12,9 @@ from synchrad_b200 import _lib, host
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, 'libsrb_emu.so')
 _SRC = [os.path.join(_HERE, 'emu.cpp'),
-        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh')]
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh'),
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_pair.cuh'),
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh')]
 
 
 def build():
