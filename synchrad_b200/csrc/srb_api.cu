@@ -161,6 +161,7 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, 3, float)
   // symmetric-pair kernel: far field, transverse basis
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 2)
+  SRB_CASE(KIND_PAIR, MODE_FAR, 1, false, 16, 2, float)      // fp32 only: 64 accumulators fit in registers
   // literal fp32 (dtype 2)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 4, 3, float)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 2, 3, float)
@@ -225,7 +226,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (p->kind == KIND_LITERAL && g->phasor == SRB_PHASOR_RECUR) return fail("the literal fp32 kernels have no recurrence variant");
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
-  else if (p->kind == KIND_PAIR) { twMax = 8; twMin = 2; }
+  else if (p->kind == KIND_PAIR) { twMax = g->dtype == SRB_DTYPE_F32 ? 16 : 8; twMin = 2; }
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }

@@ -31,10 +31,10 @@ SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, WarpSmem
   double s0, c0, sd, cd;
   sincos_big(smul(w0, tau), &s0, &c0);
   sincos_big(P.domega * tau, &sd, &cd);
-  double pr[7], pi[7];                     // R^(2^i)
+  double pr[8], pi[8];                     // R^(2^i)
   pr[0] = cd; pi[0] = sd;
 #pragma unroll
-  for (int i = 1; i < 7; i++) { pr[i] = pr[i - 1] * pr[i - 1] - pi[i - 1] * pi[i - 1]; pi[i] = 2.0 * pr[i - 1] * pi[i - 1]; }
+  for (int i = 1; i < 8; i++) { pr[i] = pr[i - 1] * pr[i - 1] - pi[i - 1] * pi[i - 1]; pi[i] = 2.0 * pr[i - 1] * pi[i - 1]; }
   // Z_b = R^b
   double zr0 = 1.0, zi0 = 0.0, zr1 = cd, zi1 = sd;
   const double cf = 2.0 * cd;
@@ -48,7 +48,7 @@ SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, WarpSmem
   // E_c = E0 * R^(16(TW-1))
   double er = c0, ei = s0;
 #pragma unroll
-  for (int i = 4; i < 7; i++) {
+  for (int i = 4; i < 8; i++) {
     if ((16 * (TW - 1)) & (1 << i)) { const double t = er * pr[i] - ei * pi[i]; ei = er * pi[i] + ei * pr[i]; er = t; }
   }
   // Y_a = E_c * R^(8a)

@@ -103,6 +103,7 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
 #undef EMU_CASE1
 #define EMU_PAIR(TWV) if (kind == KIND_PAIR && g->mode == MODE_FAR && tw == TWV && !spheric) { if (f32) run_all<Cfg<double, float, MODE_FAR, KIND_PAIR, TWV, false, 2>>(P, counters); else run_all<Cfg<double, double, MODE_FAR, KIND_PAIR, TWV, false, 2>>(P, counters); ok = true; }
   EMU_PAIR(8) EMU_PAIR(4) EMU_PAIR(2)
+  if (kind == KIND_PAIR && g->mode == MODE_FAR && tw == 16 && !spheric && f32) { run_all<Cfg<double, float, MODE_FAR, KIND_PAIR, 16, false, 2>>(P, counters); ok = true; }
 #undef EMU_PAIR
 #define EMU_LIT(M, TWV) if (kind == KIND_LITERAL && g->mode == M && tw == TWV) { run_all<Cfg<double, float, M, KIND_LITERAL, TWV, false, 3>>(P, counters); ok = true; }
   EMU_LIT(MODE_FAR, 8) EMU_LIT(MODE_FAR, 4) EMU_LIT(MODE_FAR, 2) EMU_LIT(MODE_NEAR, 8) EMU_LIT(MODE_NEAR, 4) EMU_LIT(MODE_NEAR, 2)
