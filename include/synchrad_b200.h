@@ -58,7 +58,8 @@ extern "C" {
 #define SRB_DTYPE_F32_LITERAL 2
 
 /* phasor: how exp(i*omega*tau) is evaluated per node */
-#define SRB_PHASOR_AUTO 0   /* uniform grid: pair kernel (far, non-spheric) or recurrence; else direct */
+#define SRB_PHASOR_AUTO 0   /* uniform grid: pair kernel (far, non-spheric) or recurrence, chosen from a sampled
+                               Nyquist-guard statistic (one 12-byte read-back synchronises the stream); else direct */
 #define SRB_PHASOR_DIRECT 1 /* per-node sincos of the reference's rounded phase */
 #define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
 #define SRB_PHASOR_PAIR 3   /* symmetric node pairs about the tile centre, broadcast pair phasors

@@ -85,6 +85,29 @@ __global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_
   }
 }
 
+// Guard statistics of a random sample of (track, step, direction) triples (far field): how many steps
+// pass the Nyquist guard at every node of the grid ("full"), at some nodes only ("partial"), or nowhere.
+// The pair kernel is faster on full steps (5.0 vs 6.0 FP64 ops per update) but ~3x slower on partial
+// ones (its accumulators are sums over node PAIRS), so the planner picks by this ratio.
+__global__ void k_probe(const srb::Params P, uint64_t total, double wFirst, double wLast, unsigned int* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t h = (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  const uint64_t gs = h % total;
+  uint32_t a = 0, b = P.nTracks;
+  while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (P.offsets[mid] <= gs) a = mid; else b = mid; }
+  const uint64_t o = P.offsets[a], n = P.offsets[a + 1] - o, it = gs - o;
+  if (it == 0 || it + 1 >= n) return;
+  const uint32_t d = (uint32_t)((h >> 33) % ((uint64_t)P.nA2 * P.nPhi));
+  const uint32_t iA2 = d % P.nA2, iPhi = d / P.nA2;
+  const double sT = ((const double*)P.axA)[iA2], cT = ((const double*)P.axB)[iA2];
+  const double sP = ((const double*)P.sinPhi)[iPhi], cP = ((const double*)P.cosPhi)[iPhi];
+  const double* x = (const double*)P.x; const double* y = (const double*)P.y; const double* z = (const double*)P.z;
+  const double dtau = fabs(P.dt - ((x[gs] - x[gs - 1]) * sT * cP + (y[gs] - y[gs - 1]) * sT * sP + (z[gs] - z[gs - 1]) * cT));
+  atomicAdd(out, 1u);
+  if (wLast * dtau < 3.14159265358979323846) atomicAdd(out + 1, 1u);
+  else if (wFirst * dtau < 3.14159265358979323846) atomicAdd(out + 2, 1u);
+}
+
 // out[c][i] += sum over particle chunks of the private partial spectra (fixed order: deterministic)
 __global__ void k_reduce_slabs(srb::Params P, int nOut, size_t perOut) {
   const size_t n = (size_t)nOut * perOut;
@@ -202,7 +225,8 @@ int validate(const srb_grid* g, const srb_tracks* t) {
   return 0;
 }
 
-int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool unlimited, Plan* p) {
+int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool unlimited, Plan* p,
+              bool preferRecur = false) {
   int dev = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&p->numSM, cudaDevAttrMultiProcessorCount, dev));
@@ -212,7 +236,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   const bool pairOk = uniform && g->mode == SRB_MODE_FAR && !spheric;
   if (g->phasor == SRB_PHASOR_PAIR && !pairOk) return fail("the pair kernel needs a far-field, non-spheric comp on an ascending uniform omega grid");
   if (g->phasor == SRB_PHASOR_DIRECT || !uniform) p->kind = KIND_DIRECT;
-  else if (g->phasor == SRB_PHASOR_RECUR || !pairOk) p->kind = KIND_RECUR;
+  else if (g->phasor == SRB_PHASOR_RECUR || !pairOk || (preferRecur && g->phasor == SRB_PHASOR_AUTO)) p->kind = KIND_RECUR;
   else p->kind = KIND_PAIR;
   // near field: phase = omega*(t+R) ~ omega*L.  Beyond 2^18 rad the recurrence cannot track the
   // reference's rounded phase to 1e-9 (srb_core.cuh, flag 3), every step would fall back, so the
@@ -301,8 +325,30 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
                   void* scratch, size_t scratch_bytes, uint64_t* counters, void* stream_) {
   if (validate(g, t) != 0) return -1;
   cudaStream_t stream = (cudaStream_t)stream_;
+  // Both uniform-grid kernels eligible: sample the guard statistics (one small kernel + a 12-byte read-back,
+  // the only host synchronisation of this call; an explicit `phasor` avoids it)
+  bool preferRecur = false;
+  {
+    const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
+    const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
+    unsigned int* probeBuf = (scratch && scratch_bytes >= 64) ? (unsigned int*)scratch : (unsigned int*)counters;
+    if (g->phasor == SRB_PHASOR_AUTO && uniform && g->mode == SRB_MODE_FAR && !spheric && g->dtype != SRB_DTYPE_F32_LITERAL &&
+        probeBuf && t->nTracks && t->totalSteps_host > 2) {
+      srb::Params Q;
+      std::memset(&Q, 0, sizeof Q);
+      Q.nA2 = g->nAxis2; Q.nPhi = g->nPhi; Q.axA = g->sinTheta; Q.axB = g->cosTheta; Q.sinPhi = g->sinPhi; Q.cosPhi = g->cosPhi;
+      Q.dt = g->dt; Q.nTracks = t->nTracks; Q.x = t->x; Q.y = t->y; Q.z = t->z; Q.offsets = t->offsets;
+      unsigned int h[3] = {0, 0, 0};
+      SRB_CUDA(cudaMemsetAsync(probeBuf, 0, 16, stream));
+      k_probe<<<64, 128, 0, stream>>>(Q, t->totalSteps_host, g->omega_first_host, g->omega_last_host, probeBuf);
+      SRB_CUDA(cudaGetLastError());
+      SRB_CUDA(cudaMemcpyAsync(h, probeBuf, 12, cudaMemcpyDeviceToHost, stream));
+      SRB_CUDA(cudaStreamSynchronize(stream));
+      preferRecur = h[0] > 0 && (double)h[2] > 0.1 * (double)h[1];   // partial steps cost the pair kernel ~3x
+    }
+  }
   Plan p;
-  if (make_plan(g, t, scratch ? scratch_bytes : 0, false, &p) != 0) return -1;
+  if (make_plan(g, t, scratch ? scratch_bytes : 0, false, &p, preferRecur) != 0) return -1;
   if (n_spectra != p.nOut || !spectra) return fail("n_spectra does not match comp");
   for (int c = 0; c < p.nOut; c++) if (!spectra[c]) return fail("null spectrum buffer");
   std::memset(&g_info, 0, sizeof g_info);
