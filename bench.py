@@ -144,8 +144,12 @@ def run_product(a):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    real_stdout = sys.stdout
-    sys.stdout = sys.stderr            # keep stdout for the one JSON line
+    # keep stdout for the ONE JSON line: Python prints go to stderr, and so does anything C libraries
+    # write to file descriptor 1 (NCCL prints its version banner there)
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
 
     from synchrad.calc import SynchRad
     from synchrad_b200 import _lib, engine, host, synthetic
@@ -313,8 +317,7 @@ def run_product(a):
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
-    real_stdout.write(json.dumps(line) + '\n')
-    real_stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
 
