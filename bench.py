@@ -136,6 +136,12 @@ def run_product(a):
     import torch
     import torch.distributed as dist
 
+    # keep stdout for the ONE JSON line: Python prints go to stderr, and so does anything C libraries
+    # write to file descriptor 1 (NCCL prints its version banner there)
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -144,12 +150,6 @@ def run_product(a):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    # keep stdout for the ONE JSON line: Python prints go to stderr, and so does anything C libraries
-    # write to file descriptor 1 (NCCL prints its version banner there)
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    sys.stdout = sys.stderr
 
     from synchrad.calc import SynchRad
     from synchrad_b200 import _lib, engine, host, synthetic
