@@ -288,7 +288,7 @@ def run_product(a):
         'kernel_ms_per_launch': k_ms,
         'kernel': 'k_integrate<%s, tile %d>' % (kname, info.tile_width),
         'traffic': traffic,
-        'fp64_pipe_active_ncu': 0.664 if default_cfg else None,   # sm__pipe_fp64_cycles_active of the same full-size launch
+        'fp64_pipe_active_ncu': 0.684 if default_cfg else None,   # sm__pipe_fp64_cycles_active, profiles/r01_ncu_v5_pair_final.txt
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }

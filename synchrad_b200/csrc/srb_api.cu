@@ -186,6 +186,7 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   // symmetric-pair kernel: far field, transverse basis
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 2)
   SRB_CASE(KIND_PAIR, MODE_FAR, 1, false, 16, 2, float)      // fp32 only: 64 accumulators fit in registers
+  SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 3)   // spheric kernels
   // literal fp32 (dtype 2)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 4, 3, float)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 2, 3, float)
@@ -234,8 +235,8 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
   if (g->phasor == SRB_PHASOR_RECUR && !uniform) return fail("phasor recurrence needs an ascending uniform omega grid");
   const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
-  const bool pairOk = uniform && g->mode == SRB_MODE_FAR && !spheric;
-  if (g->phasor == SRB_PHASOR_PAIR && !pairOk) return fail("the pair kernel needs a far-field, non-spheric comp on an ascending uniform omega grid");
+  const bool pairOk = uniform && g->mode == SRB_MODE_FAR;
+  if (g->phasor == SRB_PHASOR_PAIR && !pairOk) return fail("the pair kernel needs the far field and an ascending uniform omega grid");
   if (g->phasor == SRB_PHASOR_DIRECT || !uniform) p->kind = KIND_DIRECT;
   else if (g->phasor == SRB_PHASOR_RECUR || !pairOk || (preferRecur && g->phasor == SRB_PHASOR_AUTO)) p->kind = KIND_RECUR;
   else p->kind = KIND_PAIR;
@@ -251,7 +252,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (p->kind == KIND_LITERAL && g->phasor == SRB_PHASOR_RECUR) return fail("the literal fp32 kernels have no recurrence variant");
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
-  else if (p->kind == KIND_PAIR) { twMax = g->dtype == SRB_DTYPE_F32 ? 16 : 8; twMin = 2; }
+  else if (p->kind == KIND_PAIR) { twMax = (g->dtype == SRB_DTYPE_F32 && !spheric) ? 16 : 8; twMin = 2; }
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }
@@ -259,7 +260,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
     const int tw = std::atoi(f);
     if (tw >= twMin && tw <= twMax && (tw & (tw - 1)) == 0) p->tw = tw;
   }
-  p->nc = (p->kind == KIND_PAIR || (p->kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric)) ? 2 : 3;
+  p->nc = ((p->kind == KIND_PAIR || p->kind == KIND_RECUR) && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
   if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L)) return fail("internal: no kernel for this configuration");
   p->chunkNodes = (uint32_t)p->L.chunk;
   p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;
@@ -333,7 +334,7 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
     const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
     const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
     unsigned int* probeBuf = (scratch && scratch_bytes >= 64) ? (unsigned int*)scratch : (unsigned int*)counters;
-    if (g->phasor == SRB_PHASOR_AUTO && uniform && g->mode == SRB_MODE_FAR && !spheric && g->dtype != SRB_DTYPE_F32_LITERAL &&
+    if (g->phasor == SRB_PHASOR_AUTO && uniform && g->mode == SRB_MODE_FAR && g->dtype != SRB_DTYPE_F32_LITERAL &&
         probeBuf && t->nTracks && t->totalSteps_host > 2) {
       srb::Params Q;
       std::memset(&Q, 0, sizeof Q);

@@ -17,7 +17,7 @@ def test_random_problems_match_oracle(oracle, seed):
         with contextlib.redirect_stdout(io.StringIO()):
             ref = oracle.calculate_spectrum(A, tracks, dt, **kw)
         kinds = ['direct'] if A.get('Features') or A['grid'][-1][0] < 2 else ['direct', 'recur']
-        if 'recur' in kinds and A.get('mode', 'far') == 'far' and not kw['comp'].startswith('spheric'):
+        if 'recur' in kinds and A.get('mode', 'far') == 'far':
             kinds.append('pair')
         for kind in kinds:
             for nPC in (1, 3):

@@ -12,7 +12,7 @@ from emu import emu
 
 def check(oracle, args, tracks, dt, kinds=('direct', 'recur'), tol=1e-9, nPC=1, tw=None, **kw):
     ref = oracle.calculate_spectrum(args, tracks, dt, **kw)
-    if 'recur' in kinds and args.get('mode', 'far') == 'far' and not kw.get('comp', 'total').startswith('spheric'):
+    if 'recur' in kinds and args.get('mode', 'far') == 'far':
         kinds = tuple(kinds) + ('pair',)      # the symmetric-pair kernel covers the same cases
     for kind in kinds:
         rad, cnt = emu.run(args, tracks, dt, kind=kind, nPC=nPC, tw=tw if kind == 'recur' else None, **kw)

@@ -370,7 +370,7 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
         A, tracks, dt, kw = fuzzcases.rand_case(rs)
         with contextlib.redirect_stdout(io.StringIO()):
             ref = oracle.calculate_spectrum(A, tracks, dt, **kw)
-            far_plain = A.get('mode', 'far') == 'far' and not kw['comp'].startswith('spheric')
+            far_plain = A.get('mode', 'far') == 'far'
             if A.get('Features') or A['grid'][-1][0] < 2:
                 phasors = ('auto',)
             else:
