@@ -148,10 +148,13 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
         if timing:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        _lib.check(lib.srb_integrate(
+        torch.cuda.nvtx.range_push(f'srb_integrate[{mode},{comp},{n_tracks} tracks]')   # profiler ranges
+        rc = lib.srb_integrate(
             ctypes.byref(g), ctypes.byref(t), sp, n_out,
             scratch.data_ptr() if scratch is not None else None, nbytes,
-            cnt.data_ptr() if cnt is not None else None, ctypes.c_void_p(stream.cuda_stream)))
+            cnt.data_ptr() if cnt is not None else None, ctypes.c_void_p(stream.cuda_stream))
+        torch.cuda.nvtx.range_pop()
+        _lib.check(rc)
         res = Result()
         res.elapsed_ms = None
         if timing:
