@@ -241,10 +241,18 @@ struct Cfg {
       : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || KIND_ == KIND_PAIR)) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
-  //          (pair) cos/sin of the TW/2 pair offsets (flag 3: tau in the first of them)
+  //          (pair) V[NC], tau (flag 3 only), pad to QOFF, then A_c*(cos,sin) of the TW/2 pair offsets for
+  //          every component c: [QOFF + 2(p*NC + c)]; padded to a multiple of 4 (16-byte rows in fp32)
+  static constexpr int QOFF = 4;
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
-      : (((NV + (KIND_ == KIND_RECUR ? 3 : (KIND_ == KIND_PAIR ? TW_ : 1))) + 1) & ~1);
+      : KIND_ == KIND_PAIR ? ((QOFF + NC_ * TW_ + 3) & ~3)
+      : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
   static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : (KIND_ == KIND_PAIR ? 24 : 1);
+  // fp64 pair kernel on the FP64 tensor cores (DMMA.8x8x4, srb_pair.cuh): the accumulation is a GEMM
+  //   U[(tile, Re|Im X), (pair, component, cos|sin)] += X[(tile), step] * Q'[step, (pair, component)]
+  // with K = steps; it needs the column count TW*NC to be a multiple of 8 (n-tiles of the MMA).
+  static constexpr bool MMA = KIND_ == KIND_PAIR && sizeof(TM_) == 8 && (TW_ * NC_) % 8 == 0;
+  static constexpr int NT = MMA ? TW_ * NC_ / 8 : 0;            // 8-column tiles of Q'
 };
 
 template <class C>
@@ -300,8 +308,17 @@ SRB_HD void near_step_kinematics(const void* ux, const void* uy, const void* uz,
 }
 
 // pair kind (srb_pair.cuh)
-template <class C> SRB_HD void make_seeds_pair(const Params&, const Geom&, double, WarpSmem<C>&, int);
+template <class C> SRB_HD void make_seeds_pair(const Params&, const Geom&, double, const double*, WarpSmem<C>&, int);
 template <class C> SRB_HD void main_pair(const Params&, const Geom&, const WarpSmem<C>&, int, uint32_t, uint32_t, int, ThreadState<C>&);
+#if defined(__CUDA_ARCH__)
+template <class C> SRB_HD void main_pair_mma(const Params&, const Geom&, const WarpSmem<C>&, int, uint32_t, uint32_t, int, ThreadState<C>&);
+#else
+template <class C> inline void main_pair_mma(const Params&, const Geom&, const WarpSmem<C>&, int, uint32_t, uint32_t, ThreadState<C>*);
+#endif
+template <class C> SRB_HD void pair_mma_store_frag(WarpSmem<C>&, int, const ThreadState<C>&);
+template <class C> SRB_HD void pair_mma_load_frag(const WarpSmem<C>&, int, ThreadState<C>&);
+template <class C> SRB_HD void pair_mma_load_tile(const WarpSmem<C>&, int, ThreadState<C>&);
+template <class C> SRB_HD void pair_mma_store_tile(WarpSmem<C>&, int, const ThreadState<C>&);
 template <class C> SRB_HD void pair_node_amp(const ThreadState<C>&, int, double*, double*);
 // literal fp32 kind (srb_literal.cuh), used by warp_task below
 template <class C> SRB_HD void lit_prep_phase(const Params&, const Geom&, const TrackView&, uint32_t, int, int, WarpSmem<C>&);
@@ -473,7 +490,7 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   if constexpr (C::KIND == KIND_PAIR) {
     const double wl = (double)((const typename C::TI*)P.omega)[g.cHi - 1];
     if (sizeof(TM) == 8 && fabs(wl * tau) > 262144.0) flag = 3u;
-    else make_seeds_pair<C>(P, g, tau, sm, lane);
+    else make_seeds_pair<C>(P, g, tau, V, sm, lane);
   }
   if (C::KIND == KIND_RECUR) {
     // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
@@ -798,6 +815,13 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
     t0 = bound(pc); t1 = bound(pc + 1);
   }
   const double dtInv = sdiv(1.0, P.dt);
+  if constexpr (C::MMA) {
+    // masked steps of the tensor-core main phase multiply stale staging data by 0: keep it finite from the start
+    SRB_LANES_BEGIN
+      uint32_t* raw = reinterpret_cast<uint32_t*>(&sm);
+      for (uint32_t k = (uint32_t)lane; k < sizeof(WarpSmem<C>) / 4u; k += 32u) raw[k] = 0u;
+    SRB_LANES_END
+  }
   SRB_LANES_BEGIN
     SRB_ST.nPass = 0; SRB_ST.nAll = 0;
     if (C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) {
@@ -861,17 +885,45 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
           if (fl != 0u) anyMask |= 1u << lane;
 #endif
         SRB_LANES_END
+#if !defined(__CUDA_ARCH__)
+        if constexpr (C::MMA) main_pair_mma<C>(P, g, sm, cnt, fullMask, anyMask, st);   // warp-collective: emulated over all lanes
+        else
+#endif
+        {
         SRB_LANES_BEGIN
           if constexpr (C::KIND == KIND_RECUR) main_recur<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
+          else if constexpr (C::MMA) {
+#if defined(__CUDA_ARCH__)
+            main_pair_mma<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
+#endif
+          }
           else if constexpr (C::KIND == KIND_PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
         }
+        }
+      }
+      if constexpr (C::MMA) {
+        // tensor-core accumulator layout -> one tile per lane for the flush, and back (cumulative snapshots)
+        SRB_LANES_BEGIN
+          pair_mma_store_frag<C>(sm, lane, SRB_ST);
+        SRB_LANES_END
+        SRB_LANES_BEGIN
+          pair_mma_load_tile<C>(sm, lane, SRB_ST);
+        SRB_LANES_END
       }
       SRB_LANES_BEGIN
         if constexpr (C::KIND == KIND_LITERAL) lit_flush_lane<C>(P, g, tv, pc, iSnap, lane, SRB_ST);
         else flush_lane<C>(P, g, tv, pc, iSnap, lane, st);
       SRB_LANES_END
+      if constexpr (C::MMA) {
+        SRB_LANES_BEGIN
+          pair_mma_store_tile<C>(sm, lane, SRB_ST);
+        SRB_LANES_END
+        SRB_LANES_BEGIN
+          pair_mma_load_frag<C>(sm, lane, SRB_ST);
+        SRB_LANES_END
+      }
       cur = (uint32_t)(itf + 1);
       iSnap++;
     }
