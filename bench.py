@@ -266,16 +266,17 @@ def run_product(a):
     # DRAM bytes of ONE launch of this exact configuration, from an ncu capture of the same kernel
     # (dram__bytes_read.sum + dram__bytes_write.sum of the full-size launch)
     default_cfg = (a.dtype == 'double' and a.phasor == 'auto' and n_p == 12500 and n_s == 10000)
-    traffic = 25906307584 + 1754827520 if default_cfg else None   # profiles/r01_ncu_full_size_launch_metrics_pair.csv
+    traffic = 24439411200 + 475320320 if default_cfg else None   # profiles/r01_ncu_full_size_launch_metrics_dmma.csv
     slots_alg = ALG_SLOTS[a.dtype]
     achieved = updates_rank * slots_alg / (k_ms * 1e-3)          # algorithmic slots/s of one launch
     issued = None
     tw, nc = int(info.tile_width), int(info.n_components)
     if int(info.kind) == 1:      # recurrence: per lane and step (TW-2) chain + NC*TW accumulate + 2 seed ops, for TW half-updates
         issued = 2.0 * ((tw - 2) + nc * tw + 2) / tw
-    elif int(info.kind) == 3:    # pair: per lane and step 4 (X = Y*Z) + 2*NC (B = A*X) + 4*NC*TW/2 accumulate, for TW updates
-        issued = (4 + 2 * nc + 2 * nc * tw) / tw
-    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair'}[int(info.kind)]
+    elif int(info.kind) == 3:    # pair: per lane and step 4 (X = Y*Z) + 4*NC*TW/2 accumulate FMAs, for TW updates;
+        issued = (4 + 2 * nc * tw) / tw   # fp64 with TW*NC % 8 == 0: the accumulate FMAs are issued as DMMA.8x8x4 (256 each)
+    mma = int(info.kind) == 3 and a.dtype == 'double' and (tw * nc) % 8 == 0
+    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair, DMMA' if mma else 'pair'}[int(info.kind)]
     roofline = {
         'bound': 'fp64_pipe' if a.dtype == 'double' else 'fp32_pipe',
         'achieved': achieved / 1e12, 'peak': peak.value / 1e12, 'unit': 'Tslot/s (FMA-pipe lane issue slots)',
@@ -288,7 +289,10 @@ def run_product(a):
         'kernel_ms_per_launch': k_ms,
         'kernel': 'k_integrate<%s, tile %d>' % (kname, info.tile_width),
         'traffic': traffic,
-        'fp64_pipe_active_ncu': 0.684 if default_cfg else None,   # sm__pipe_fp64_cycles_active, profiles/r01_ncu_v5_pair_final.txt
+        # full-size ncu pass (profiles/r01_ncu_full_size_launch_metrics_dmma.csv): 5.12e11 DMMA.8x8x4 warp-instructions
+        # x 16 cycles / (592 sub-partitions x 2.378e10 cycles) = 0.582 of the FP64 units' time in DMMA, plus
+        # sm__pipe_fp64_cycles_active = 0.190 for the DFMA/DMUL stream (X = Y*Z and the prep phase)
+        'fp64_units_busy_ncu': {'dmma': 0.582, 'dfma_pipe': 0.190} if default_cfg else None,
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }

@@ -35,6 +35,9 @@ int fail(const std::string& m) { g_err = m; return -1; }
 #ifndef SRB_MINB
 #define SRB_MINB 4
 #endif
+#ifndef SRB_MINB_MMA
+#define SRB_MINB_MMA 3
+#endif
 #ifndef SRB_MINB_DIRECT
 #define SRB_MINB_DIRECT 2
 #endif
@@ -44,6 +47,7 @@ constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
   if (C::KIND == srb::KIND_DIRECT || C::KIND == srb::KIND_LITERAL) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
+  if (C::MMA) return SRB_MINB_MMA;
   if (C::KIND == srb::KIND_PAIR && sizeof(typename C::TM) == 8) return SRB_MINB > 3 ? 3 : SRB_MINB;   // measured: 168 regs beat 128
   return accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB);
 }
