@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the spectral-integration hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype double|float] [--phasor auto|direct]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype double|float] [--phasor auto|direct|recur|pair|pair_fma]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
 
@@ -275,8 +275,10 @@ def run_product(a):
         issued = 2.0 * ((tw - 2) + nc * tw + 2) / tw
     elif int(info.kind) == 3:    # pair: per lane and step 4 (X = Y*Z) + 4*NC*TW/2 accumulate FMAs, for TW updates;
         issued = (4 + 2 * nc * tw) / tw   # fp64 with TW*NC % 8 == 0: the accumulate FMAs are issued as DMMA.8x8x4 (256 each)
+    elif int(info.kind) == 4:    # pair kernel kept on the scalar pipe
+        issued = (4 + 2 * nc * tw) / tw
     mma = int(info.kind) == 3 and a.dtype == 'double' and (tw * nc) % 8 == 0
-    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair, DMMA' if mma else 'pair'}[int(info.kind)]
+    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair, DMMA' if mma else 'pair', 4: 'pair, DFMA'}[int(info.kind)]
     roofline = {
         'bound': 'fp64_pipe' if a.dtype == 'double' else 'fp32_pipe',
         'achieved': achieved / 1e12, 'peak': peak.value / 1e12, 'unit': 'Tslot/s (FMA-pipe lane issue slots)',
@@ -333,7 +335,7 @@ def main():
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--dtype', default='double', choices=['double', 'float'])
-    p.add_argument('--phasor', default='auto', choices=['auto', 'direct', 'recur', 'pair'])
+    p.add_argument('--phasor', default='auto', choices=['auto', 'direct', 'recur', 'pair', 'pair_fma'])
     p.add_argument('--particles-per-gpu', type=int, default=12500)
     p.add_argument('--track-steps', type=int, default=10000)
     p.add_argument('--e2e-steps', type=int, default=2)

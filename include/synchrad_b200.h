@@ -62,8 +62,10 @@ extern "C" {
                                Nyquist-guard statistic (one 12-byte read-back synchronises the stream); else direct */
 #define SRB_PHASOR_DIRECT 1 /* per-node sincos of the reference's rounded phase */
 #define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
-#define SRB_PHASOR_PAIR 3   /* symmetric node pairs about the tile centre, broadcast pair phasors
-                               (uniform grids, far field, total/cartesian/cartesian_complex) */
+#define SRB_PHASOR_PAIR 3   /* symmetric node pairs about the tile centre, broadcast pair phasors (uniform grids, far
+                               field); fp64: the accumulation over steps runs as a GEMM on the FP64 tensor cores
+                               (DMMA.8x8x4) when tile width x components is a multiple of 8 */
+#define SRB_PHASOR_PAIR_FMA 4 /* the pair kernel with the accumulation kept on the scalar FP64 pipe (DFMA) */
 
 /* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
  * Tables are float64 arrays with the content `_init_data` uploads (calc.py:486-512): omega is

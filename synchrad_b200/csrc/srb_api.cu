@@ -48,7 +48,7 @@ template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
   if (C::KIND == srb::KIND_DIRECT || C::KIND == srb::KIND_LITERAL) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
   if (C::MMA) return SRB_MINB_MMA;
-  if (C::KIND == srb::KIND_PAIR && sizeof(typename C::TM) == 8) return SRB_MINB > 3 ? 3 : SRB_MINB;   // measured: 168 regs beat 128
+  if (C::PAIR && sizeof(typename C::TM) == 8) return SRB_MINB > 3 ? 3 : SRB_MINB;   // measured: 168 regs beat 128
   return accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB);
 }
 
@@ -166,7 +166,7 @@ template <class C> Launcher make_launcher() {
   return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK};
 }
 
-using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::MODE_FAR; using srb::MODE_NEAR;
+using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::KIND_PAIR_FMA; using srb::MODE_FAR; using srb::MODE_NEAR;
 
 // kind, mode, dtype, native, tile width, far components -> kernel
 bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* L) {
@@ -191,6 +191,9 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 2)
   SRB_CASE(KIND_PAIR, MODE_FAR, 1, false, 16, 2, float)      // fp32 only: 64 accumulators fit in registers
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 3)   // spheric kernels
+  // the same kernel without tensor cores, where KIND_PAIR uses them (fp64, TW*NC % 8 == 0); phasor = SRB_PHASOR_PAIR_FMA
+  SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 8, 2, double) SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 4, 2, double)
+  SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 8, 3, double)
   // literal fp32 (dtype 2)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 4, 3, float)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 2, 3, float)
@@ -240,7 +243,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (g->phasor == SRB_PHASOR_RECUR && !uniform) return fail("phasor recurrence needs an ascending uniform omega grid");
   const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
   const bool pairOk = uniform && g->mode == SRB_MODE_FAR;
-  if (g->phasor == SRB_PHASOR_PAIR && !pairOk) return fail("the pair kernel needs the far field and an ascending uniform omega grid");
+  if ((g->phasor == SRB_PHASOR_PAIR || g->phasor == SRB_PHASOR_PAIR_FMA) && !pairOk) return fail("the pair kernel needs the far field and an ascending uniform omega grid");
   if (g->phasor == SRB_PHASOR_DIRECT || !uniform) p->kind = KIND_DIRECT;
   else if (g->phasor == SRB_PHASOR_RECUR || !pairOk || (preferRecur && g->phasor == SRB_PHASOR_AUTO)) p->kind = KIND_RECUR;
   else p->kind = KIND_PAIR;
@@ -265,6 +268,9 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
     if (tw >= twMin && tw <= twMax && (tw & (tw - 1)) == 0) p->tw = tw;
   }
   p->nc = ((p->kind == KIND_PAIR || p->kind == KIND_RECUR) && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
+  // SRB_PHASOR_PAIR_FMA: scalar-pipe accumulation; only differs where the pair kernel would use DMMA
+  if (g->phasor == SRB_PHASOR_PAIR_FMA && p->kind == KIND_PAIR && g->dtype == SRB_DTYPE_F64 && (p->tw * p->nc) % 8 == 0)
+    p->kind = KIND_PAIR_FMA;
   if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L)) return fail("internal: no kernel for this configuration");
   p->chunkNodes = (uint32_t)p->L.chunk;
   p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;

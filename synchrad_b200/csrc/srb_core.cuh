@@ -57,7 +57,8 @@ namespace srb {
 
 enum { MODE_FAR = 0, MODE_NEAR = 1 };
 enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
-enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh
+enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3, KIND_PAIR_FMA = 4 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh
+// KIND_PAIR_FMA: the pair kernel with its accumulation on the scalar FP64 pipe (DFMA) where KIND_PAIR uses DMMA
 constexpr int SUB = 32;  // steps per sub-batch (= lanes of the prep phase)
 
 // ---- strict (uncontracted, round-to-nearest) double arithmetic: the oracle's operation order
@@ -231,6 +232,7 @@ struct Cfg {
   using TI = TI_;   // dtype of tables / tracks
   using TM = TM_;   // arithmetic type of the main phase
   static constexpr int MODE = MODE_, KIND = KIND_, TW = TW_, NC = NC_;
+  static constexpr bool PAIR = KIND_ == KIND_PAIR || KIND_ == KIND_PAIR_FMA;
   static constexpr bool NATIVE = NATIVE_;
   static constexpr int TILES = (KIND_ == KIND_RECUR) ? 16 : 32;   // omega tiles per chunk
   static constexpr int CHUNK = TILES * TW_;
@@ -238,16 +240,16 @@ struct Cfg {
   // accumulators per node: split layout (recurrence) holds one part (cos or sin) of NV sums,
   // the direct layout holds Re and Im of the 3 (far: NC) amplitude components
   static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV
-      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || KIND_ == KIND_PAIR)) ? 2 * NC_ : 6);
+      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || PAIR)) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
   //          (pair) V[NC], tau (flag 3 only), pad to QOFF, then A_c*(cos,sin) of the TW/2 pair offsets for
   //          every component c: [QOFF + 2(p*NC + c)]; padded to a multiple of 4 (16-byte rows in fp32)
   static constexpr int QOFF = 4;
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
-      : KIND_ == KIND_PAIR ? ((QOFF + NC_ * TW_ + 3) & ~3)
+      : PAIR ? ((QOFF + NC_ * TW_ + 3) & ~3)
       : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
-  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : (KIND_ == KIND_PAIR ? 24 : 1);
+  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : (PAIR ? 24 : 1);
   // fp64 pair kernel on the FP64 tensor cores (DMMA.8x8x4, srb_pair.cuh): the accumulation is a GEMM
   //   U[(tile, Re|Im X), (pair, component, cos|sin)] += X[(tile), step] * Q'[step, (pair, component)]
   // with K = steps; it needs the column count TW*NC to be a multiple of 8 (n-tiles of the MMA).
@@ -411,7 +413,7 @@ SRB_HD void pass_range(const Params& P, const Geom& g, double tau, double tauPre
   const uint32_t jLarge = P.descending ? g.cLo : g.cHi - 1;
   if (pass(jLarge)) { lo = 0; hi = n; return; }
   if (!pass(jSmall)) { lo = 0; hi = 0; return; }
-  if (C::KIND == KIND_RECUR || C::KIND == KIND_PAIR) {
+  if (C::KIND == KIND_RECUR || C::PAIR) {
     // uniform ascending grid: estimate the boundary from pi/|dtau|, then settle it with the exact
     // predicate (a couple of evaluations instead of a full bisection)
     const double je = (3.14159265358979323846 / fabs(ssub(tau, tauPrev)) - (double)om[g.cLo]) / P.domega;
@@ -487,7 +489,7 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, V);
   else prep_near<C>(P, g, tv, it, r0, r1, r2, rL, V, V + 3);
   double last[3] = {tau, 0.0, 0.0};
-  if constexpr (C::KIND == KIND_PAIR) {
+  if constexpr (C::PAIR) {
     const double wl = (double)((const typename C::TI*)P.omega)[g.cHi - 1];
     if (sizeof(TM) == 8 && fabs(wl * tau) > 262144.0) flag = 3u;
     else make_seeds_pair<C>(P, g, tau, V, sm, lane);
@@ -504,7 +506,7 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   st.nPass += hi - lo;
 #pragma unroll
   for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
-  if (C::KIND != KIND_PAIR || flag == 3u)
+  if (!C::PAIR || flag == 3u)
     sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau ; pair: flag 3 only
   if (C::KIND == KIND_RECUR) { sm.rec[lane][C::NV + 1] = (TM)last[1]; sm.rec[lane][C::NV + 2] = (TM)last[2]; }
   return flag;
@@ -708,7 +710,7 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
     const bool valid = j < g.cHi;
     const size_t idx = (size_t)j + (size_t)P.nOmega * (g.iA2 + (size_t)P.nA2 * g.iPhi) + nTotal * iSnap;
     double re[3], im[3];
-    if constexpr (C::KIND == KIND_PAIR) {
+    if constexpr (C::PAIR) {
       pair_node_amp<C>(me, k, re, im);
     } else if constexpr (C::KIND == KIND_DIRECT) {
 #pragma unroll
@@ -897,7 +899,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
             main_pair_mma<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
 #endif
           }
-          else if constexpr (C::KIND == KIND_PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
+          else if constexpr (C::PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
         }

@@ -108,6 +108,12 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   EMU_PAIR(8) EMU_PAIR(4) EMU_PAIR(2)
   if (kind == KIND_PAIR && g->mode == MODE_FAR && tw == 16 && !spheric && f32) { run_all<Cfg<double, float, MODE_FAR, KIND_PAIR, 16, false, 2>>(P, counters); ok = true; }
 #undef EMU_PAIR
+  // scalar-pipe form of the fp64 pair kernel where KIND_PAIR takes the tensor-core layout
+  if (kind == KIND_PAIR_FMA && g->mode == MODE_FAR && !f32) {
+    if (tw == 8 && !spheric) { run_all<Cfg<double, double, MODE_FAR, KIND_PAIR_FMA, 8, false, 2>>(P, counters); ok = true; }
+    if (tw == 4 && !spheric) { run_all<Cfg<double, double, MODE_FAR, KIND_PAIR_FMA, 4, false, 2>>(P, counters); ok = true; }
+    if (tw == 8 && spheric) { run_all<Cfg<double, double, MODE_FAR, KIND_PAIR_FMA, 8, false, 3>>(P, counters); ok = true; }
+  }
 #define EMU_LIT(M, TWV) if (kind == KIND_LITERAL && g->mode == M && tw == TWV) { run_all<Cfg<double, float, M, KIND_LITERAL, TWV, false, 3>>(P, counters); ok = true; }
   EMU_LIT(MODE_FAR, 8) EMU_LIT(MODE_FAR, 4) EMU_LIT(MODE_FAR, 2) EMU_LIT(MODE_NEAR, 8) EMU_LIT(MODE_NEAR, 4) EMU_LIT(MODE_NEAR, 2)
 #undef EMU_LIT

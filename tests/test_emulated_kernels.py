@@ -77,6 +77,20 @@ def test_omega_chunking_and_tile_widths(oracle, grid, tw):
     check(oracle, cases.c5_args(grid=grid), tr, dt, kinds=kinds, tw=tw)
 
 
+def test_pair_kernel_scalar_and_tensor_core_forms_agree(oracle):
+    """KIND_PAIR (DMMA layout for fp64, TW*NC % 8 == 0) and KIND_PAIR_FMA (one tile per lane) are the same
+    sums in a different association: both within tolerance of the oracle, and of each other far below it."""
+    tr, dt, info = cases.undulator_tracks(2, seed=3)
+    for grid, comp, tw in (((256, 3, 2), 'total', 8), ((100, 3, 2), 'cartesian', 4), ((200, 3, 2), 'spheric', 8)):
+        args = cases.undulator_args(info, grid=grid)
+        ref = oracle.calculate_spectrum(args, tr, dt, comp=comp, nSnaps=2)['radiation']
+        a, _ = emu.run(args, tr, dt, kind='pair', tw=tw, comp=comp, nSnaps=2)
+        b, _ = emu.run(args, tr, dt, kind='pair_fma', tw=tw, comp=comp, nSnaps=2)
+        for key in ref:
+            assert max(rel_errors(a[key], ref[key])) < 1e-9 and max(rel_errors(b[key], ref[key])) < 1e-9
+            assert max(rel_errors(a[key], b[key])) < 1e-12, (grid, comp, key)
+
+
 def test_guard_dominated_wiggler(oracle):
     tr, dt, info = cases.wiggler_tracks(4, 200)
     ref, cnt = check(oracle, cases.wiggler_args(info, grid=(256, 4, 3)), tr, dt, comp='cartesian', nPC=2)

@@ -119,9 +119,40 @@ def test_c3_like_si_units(cuda_lib, oracle):
 def test_c5_like_small(cuda_lib, oracle):
     tracks, dt = cases.c5_tracks_numpy(6, 1500)
     args = cases.c5_args(grid=(256, 8, 8))
-    for phasor in ('auto', 'recur', 'direct'):
+    ref = oracle.calculate_spectrum(args, tracks, dt)['radiation']
+    kernels = {}
+    for phasor in ('auto', 'pair_fma', 'recur', 'direct'):
         calc = run_gpu(args, tracks, dt, phasor=phasor)
-        assert_close(calc, oracle.calculate_spectrum(args, tracks, dt)['radiation'], what=phasor)
+        assert_close(calc, ref, what=phasor)
+        kernels[phasor] = calc.last_run['kernel']
+    # 'auto' = pair kernel on the FP64 tensor cores; 'pair_fma' = the same kernel on the scalar FP64 pipe
+    assert kernels == {'auto': 'pair', 'pair_fma': 'pair_fma', 'recur': 'recurrence', 'direct': 'direct'}
+
+
+def test_pair_kernel_tensor_core_path_forced(cuda_lib, oracle):
+    """phasor='pair' forced where 'auto' would pick the recurrence kernel: the DMMA main phase (srb_pair.cuh,
+    main_pair_mma) with most steps masked out and handled by the lane-by-lane partial path, the big-phase
+    fallback (flag 3), three components (NT = 3), ragged chunks, snapshots (layout transposes around the flush)."""
+    # guard-dominated wiggler: partial steps dominate; identical guard decisions
+    tracks, dt, info = cases.wiggler_tracks(8, 256)
+    for grid, comp in (((256, 6, 4), 'cartesian'), ((300, 5, 3), 'spheric'), ((130, 4, 3), 'total')):
+        args = cases.wiggler_args(info, grid=grid)
+        calc = run_gpu(args, tracks, dt, phasor='pair', comp=comp, nSnaps=3)
+        ref = oracle.calculate_spectrum(args, tracks, dt, comp=comp, nSnaps=3)
+        assert calc.last_run['kernel'] == 'pair' and calc.last_run['tile_width'] == 8
+        assert_close(calc, ref['radiation'], what=(grid, comp))
+        assert calc.last_run['passed_updates'] == ref['passed']
+    # SI units: |phase| > 2^18 -> per-node evaluation inside the pair layout
+    tracks, dt, info = cases.wiggler_tracks(4, 256, si_scale=1e-3)
+    args = cases.wiggler_args(info, grid=(256, 4, 4), si_scale=1e-3)
+    calc = run_gpu(args, tracks, dt, phasor='pair', comp='cartesian_complex')
+    assert_close(calc, oracle.calculate_spectrum(args, tracks, dt, comp='cartesian_complex')['radiation'])
+    # all-pass undulator with snapshots and a global iteration range, 3 components
+    tracks, dt, info = cases.undulator_tracks(3, seed=5)
+    args = cases.undulator_args(info, grid=(256, 6, 4))
+    calc = run_gpu(args, tracks, dt, phasor='pair', comp='spheric_complex', nSnaps=4, it_range=(0, 1500))
+    assert_close(calc, oracle.calculate_spectrum(args, tracks, dt, comp='spheric_complex', nSnaps=4,
+                                                 it_range=(0, 1500))['radiation'])
 
 
 # ---------------------------------------------------------------------------- golden fixtures
