@@ -876,6 +876,23 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
             lit_main_phase<C>(P, g, sm, cnt, lane, SRB_ST);
           SRB_LANES_END
         } else {
+#if defined(__CUDA_ARCH__)
+        // the prep phase of the NEXT sub-batch starts with dependent global loads: warm L1 during this main phase
+        // (measured +2 % on the C5 shard)
+        if (base + SUB < stop) {
+          const uint32_t itn = base + SUB + (threadIdx.x & 31u);
+          if (itn < stop) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const TI*)tv.x + itn));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const TI*)tv.y + itn));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const TI*)tv.z + itn));
+            if (tv.pre) {
+#pragma unroll
+              for (int c = 0; c < (C::MODE == MODE_FAR ? 6 : 3); c++)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(tv.pre + c * P.preStride + itn));
+            }
+          }
+        }
+#endif
         uint32_t fullMask = 0u, anyMask = 0u;   // bit s: step s of the sub-batch is all-pass / has any pass
         SRB_LANES_BEGIN
           const uint32_t fl = prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);

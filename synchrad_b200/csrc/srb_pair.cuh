@@ -28,7 +28,11 @@ template <class C>
 SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, const double* V, WarpSmem<C>& sm, int s) {
   using TI = typename C::TI; using TM = typename C::TM;
   constexpr int TW = C::TW;
-  const double w0 = (double)((const TI*)P.omega)[g.cLo];
+  // Phase of tile 0's centre.  It is node cLo + 16(TW-1) of the table when the chunk has that many nodes (the
+  // exact rounded phase the reference forms there, and no shift products); else node cLo shifted by R^(16(TW-1)).
+  constexpr uint32_t CEN = 16u * (uint32_t)(TW - 1);
+  const bool haveCentre = g.cLo + CEN < P.nOmega;
+  const double w0 = (double)((const TI*)P.omega)[haveCentre ? g.cLo + CEN : g.cLo];
   double s0, c0, sd, cd;
   sincos_big(smul(w0, tau), &s0, &c0);
   sincos_big(P.domega * tau, &sd, &cd);
@@ -50,7 +54,7 @@ SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, const do
   double er = c0, ei = s0;
 #pragma unroll
   for (int i = 4; i < 8; i++) {
-    if ((16 * (TW - 1)) & (1 << i)) { const double t = er * pr[i] - ei * pi[i]; ei = er * pi[i] + ei * pr[i]; er = t; }
+    if (!haveCentre && ((16 * (TW - 1)) & (1 << i))) { const double t = er * pr[i] - ei * pi[i]; ei = er * pi[i] + ei * pr[i]; er = t; }
   }
   // Y_a = E_c * R^(8a)
 #pragma unroll
