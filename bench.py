@@ -266,7 +266,7 @@ def run_product(a):
     # DRAM bytes of ONE launch of this exact configuration, from an ncu capture of the same kernel
     # (dram__bytes_read.sum + dram__bytes_write.sum of the full-size launch)
     default_cfg = (a.dtype == 'double' and a.phasor == 'auto' and n_p == 12500 and n_s == 10000)
-    traffic = 24439411200 + 475320320 if default_cfg else None   # profiles/r01_ncu_full_size_launch_metrics_dmma.csv
+    traffic = 29002931968 + 649213952 if default_cfg else None   # profiles/r01_ncu_full_size_launch_metrics_dmma.csv
     slots_alg = ALG_SLOTS[a.dtype]
     achieved = updates_rank * slots_alg / (k_ms * 1e-3)          # algorithmic slots/s of one launch
     issued = None
@@ -292,9 +292,9 @@ def run_product(a):
         'kernel': 'k_integrate<%s, tile %d>' % (kname, info.tile_width),
         'traffic': traffic,
         # full-size ncu pass (profiles/r01_ncu_full_size_launch_metrics_dmma.csv): 5.12e11 DMMA.8x8x4 warp-instructions
-        # x 16 cycles / (592 sub-partitions x 2.378e10 cycles) = 0.582 of the FP64 units' time in DMMA, plus
-        # sm__pipe_fp64_cycles_active = 0.190 for the DFMA/DMUL stream (X = Y*Z and the prep phase)
-        'fp64_units_busy_ncu': {'dmma': 0.582, 'dfma_pipe': 0.190} if default_cfg else None,
+        # x 16 cycles / (592 sub-partitions x 2.324e10 cycles) = 0.595 of the FP64 units' time in DMMA, plus
+        # sm__pipe_fp64_cycles_active = 0.185 for the DFMA/DMUL stream (X = Y*Z and the prep phase)
+        'fp64_units_busy_ncu': {'dmma': 0.595, 'dfma_pipe': 0.185} if default_cfg else None,
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }
