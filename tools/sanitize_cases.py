@@ -26,4 +26,12 @@ for dtype in ('double', 'float'):
 trw, dtw, infow = cases.wiggler_tracks(4, 100)
 out.append(run(cases.wiggler_args(infow, grid=(300, 3, 2)), trw, dtw))
 out.append(run(cases.wiggler_args(infow, grid=(100, 3, 2), features=['logGrid']), trw, dtw))
+# tensor-core pair kernel: 8-node tiles with 2 and 3 components, snapshots (layout transposes), partial path, scalar form
+for grid, comp in (((256, 3, 2), 'total'), ((300, 3, 2), 'spheric_complex')):
+    a = cases.undulator_args(info, grid=grid); a['phasor'] = 'pair'
+    out.append(run(a, short, dt, comp=comp, nSnaps=3, it_range=(0, 190)))
+w = cases.wiggler_args(infow, grid=(256, 3, 2)); w['phasor'] = 'pair'
+out.append(run(w, trw, dtw, comp='cartesian', nSnaps=2))
+a = cases.undulator_args(info, grid=(256, 3, 2)); a['phasor'] = 'pair_fma'
+out.append(run(a, short, dt, nSnaps=2))
 print('sanitize cases done', len(out), np.isfinite(out).all())
