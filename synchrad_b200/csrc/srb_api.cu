@@ -47,7 +47,7 @@ constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
   if (C::KIND == srb::KIND_DIRECT || C::KIND == srb::KIND_LITERAL) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
-  if (C::MMA) return SRB_MINB_MMA;
+  if (C::MMA) return C::NACC > 48 ? 2 : SRB_MINB_MMA;   // 16-node tiles: 64 fp64 accumulators per lane
   if (C::PAIR && sizeof(typename C::TM) == 8) return SRB_MINB > 3 ? 3 : SRB_MINB;   // measured: 168 regs beat 128
   return accRegs <= 64 ? SRB_MINB : (SRB_MINB > 3 ? 3 : SRB_MINB);
 }
@@ -189,7 +189,7 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   SRB_CASE(KIND_DIRECT, MODE_NEAR, 1, true, 2, 3, float)
   // symmetric-pair kernel: far field, transverse basis
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 2) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 2)
-  SRB_CASE(KIND_PAIR, MODE_FAR, 1, false, 16, 2, float)      // fp32 only: 64 accumulators fit in registers
+  SRB_BOTH(KIND_PAIR, MODE_FAR, false, 16, 2)      // grids with > 256 omega nodes (fp64: tensor-core layout, 2 blocks/SM)
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 3)   // spheric kernels
   // the same kernel without tensor cores, where KIND_PAIR uses them (fp64, TW*NC % 8 == 0); phasor = SRB_PHASOR_PAIR_FMA
   SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 8, 2, double) SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 4, 2, double)
@@ -259,7 +259,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (p->kind == KIND_LITERAL && g->phasor == SRB_PHASOR_RECUR) return fail("the literal fp32 kernels have no recurrence variant");
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
-  else if (p->kind == KIND_PAIR) { twMax = (g->dtype == SRB_DTYPE_F32 && !spheric) ? 16 : 8; twMin = 2; }
+  else if (p->kind == KIND_PAIR) { twMax = !spheric ? 16 : 8; twMin = 2; }
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }

@@ -245,16 +245,20 @@ struct Cfg {
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
   //          (pair) V[NC], tau (flag 3 only), pad to QOFF, then A_c*(cos,sin) of the TW/2 pair offsets for
   //          every component c: [QOFF + 2(p*NC + c)]; padded to a multiple of 4 (16-byte rows in fp32)
-  static constexpr int QOFF = 4;
-  static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
-      : PAIR ? ((QOFF + NC_ * TW_ + 3) & ~3)
-      : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
-  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : (PAIR ? 24 : 1);
   // fp64 pair kernel on the FP64 tensor cores (DMMA.8x8x4, srb_pair.cuh): the accumulation is a GEMM
   //   U[(tile, Re|Im X), (pair, component, cos|sin)] += X[(tile), step] * Q'[step, (pair, component)]
   // with K = steps; it needs the column count TW*NC to be a multiple of 8 (n-tiles of the MMA).
   static constexpr bool MMA = KIND_ == KIND_PAIR && sizeof(TM_) == 8 && (TW_ * NC_) % 8 == 0;
   static constexpr int NT = MMA ? TW_ * NC_ / 8 : 0;            // 8-column tiles of Q'
+  static constexpr int QOFF = 4;
+  static constexpr int NSEED = (KIND_ == KIND_RECUR) ? 32 : (PAIR ? 24 : 1);
+  // the tensor-core layout transposes its accumulators through the staging area at a flush: 32*NACC values
+  // must fit in rec + rng + seeds (only the 16-node tiles need the extra row padding)
+  static constexpr int NREC_PAIR = (QOFF + NC_ * TW_ + 3) & ~3;
+  static constexpr int NREC_FLUSH = MMA ? (((32 * NACC - 16 - NSEED * 33 + 31) / 32 + 3) & ~3) : 0;
+  static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
+      : PAIR ? (NREC_PAIR > NREC_FLUSH ? NREC_PAIR : NREC_FLUSH)
+      : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
 };
 
 template <class C>

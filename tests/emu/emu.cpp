@@ -105,8 +105,7 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   EMU_PAIR3(8) EMU_PAIR3(4) EMU_PAIR3(2)
 #undef EMU_PAIR3
 #define EMU_PAIR(TWV) if (kind == KIND_PAIR && g->mode == MODE_FAR && tw == TWV && !spheric) { if (f32) run_all<Cfg<double, float, MODE_FAR, KIND_PAIR, TWV, false, 2>>(P, counters); else run_all<Cfg<double, double, MODE_FAR, KIND_PAIR, TWV, false, 2>>(P, counters); ok = true; }
-  EMU_PAIR(8) EMU_PAIR(4) EMU_PAIR(2)
-  if (kind == KIND_PAIR && g->mode == MODE_FAR && tw == 16 && !spheric && f32) { run_all<Cfg<double, float, MODE_FAR, KIND_PAIR, 16, false, 2>>(P, counters); ok = true; }
+  EMU_PAIR(16) EMU_PAIR(8) EMU_PAIR(4) EMU_PAIR(2)
 #undef EMU_PAIR
   // scalar-pipe form of the fp64 pair kernel where KIND_PAIR takes the tensor-core layout
   if (kind == KIND_PAIR_FMA && g->mode == MODE_FAR && !f32) {

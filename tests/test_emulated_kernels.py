@@ -69,7 +69,7 @@ def test_flush_chain_quirks(oracle):
     check(oracle, args, short, dt, nSnaps=2, it_range=(0, 25))
 
 
-@pytest.mark.parametrize('grid,tw', [((256, 3, 2), 16), ((300, 3, 2), 16), ((128, 3, 2), 8), ((36, 3, 2), 4),
+@pytest.mark.parametrize('grid,tw', [((256, 3, 2), 16), ((300, 3, 2), 16), ((128, 3, 2), 8), ((36, 3, 2), 4), ((600, 2, 2), 16),
                                      ((1, 3, 2), None), ((2, 2, 1), None)])
 def test_omega_chunking_and_tile_widths(oracle, grid, tw):
     tr, dt = cases.c5_tracks_numpy(2, 300)

@@ -147,6 +147,12 @@ def test_pair_kernel_tensor_core_path_forced(cuda_lib, oracle):
     args = cases.wiggler_args(info, grid=(256, 4, 4), si_scale=1e-3)
     calc = run_gpu(args, tracks, dt, phasor='pair', comp='cartesian_complex')
     assert_close(calc, oracle.calculate_spectrum(args, tracks, dt, comp='cartesian_complex')['radiation'])
+    # 16-node tiles (grids with more than 256 omega nodes): 64 accumulators per lane, ragged second chunk
+    tracks, dt = cases.c5_tracks_numpy(3, 900)
+    args = cases.c5_args(grid=(600, 4, 3))
+    calc = run_gpu(args, tracks, dt, phasor='pair', nSnaps=2)
+    assert calc.last_run['kernel'] == 'pair' and calc.last_run['tile_width'] == 16
+    assert_close(calc, oracle.calculate_spectrum(args, tracks, dt, nSnaps=2)['radiation'])
     # all-pass undulator with snapshots and a global iteration range, 3 components
     tracks, dt, info = cases.undulator_tracks(3, seed=5)
     args = cases.undulator_args(info, grid=(256, 6, 4))
