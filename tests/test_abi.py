@@ -47,6 +47,16 @@ def test_struct_layouts_match_header():
         assert fields == [f[0] for f in cls._fields_], (cname, fields)
 
 
+def test_enum_constants_match_header():
+    """SRB_PHASOR_* / SRB_DTYPE_* values in the header are the ones the ctypes layer sends."""
+    from synchrad_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'synchrad_b200.h')).read()
+    defs = {k: int(v) for k, v in re.findall(r'#define\s+(SRB_[A-Z0-9_]+)\s+(\d+)', text)}
+    assert {k: defs['SRB_PHASOR_' + k.upper()] for k in _lib.PHASOR} == _lib.PHASOR
+    assert len([k for k in defs if k.startswith('SRB_PHASOR_')]) == len(_lib.PHASOR)
+    assert defs['SRB_DTYPE_F64'] == 0 and defs['SRB_DTYPE_F32'] == 1 and defs['SRB_DTYPE_F32_LITERAL'] == 2
+
+
 def test_host_only_entry_points():
     from synchrad_b200 import _lib
     lib = _lib.load()
