@@ -28,18 +28,18 @@ template <class C>
 SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, const double* V, WarpSmem<C>& sm, int s) {
   using TI = typename C::TI; using TM = typename C::TM;
   constexpr int TW = C::TW;
-  // Phase of tile 0's centre.  It is node cLo + 16(TW-1) of the table when the chunk has that many nodes (the
-  // exact rounded phase the reference forms there, and no shift products); else node cLo shifted by R^(16(TW-1)).
+  // Phase of tile 0's centre: node cLo + 16(TW-1) of the table when the chunk has that many nodes (the exact
+  // rounded phase the reference forms there), else the same frequency extrapolated on the uniform grid.
   constexpr uint32_t CEN = 16u * (uint32_t)(TW - 1);
-  const bool haveCentre = g.cLo + CEN < P.nOmega;
-  const double w0 = (double)((const TI*)P.omega)[haveCentre ? g.cLo + CEN : g.cLo];
-  double s0, c0, sd, cd;
-  sincos_big(smul(w0, tau), &s0, &c0);
+  const double wc = g.cLo + CEN < P.nOmega ? (double)((const TI*)P.omega)[g.cLo + CEN]
+                                           : (double)((const TI*)P.omega)[g.cLo] + (double)CEN * P.domega;
+  double er, ei, sd, cd;
+  sincos_big(smul(wc, tau), &ei, &er);
   sincos_big(P.domega * tau, &sd, &cd);
-  double pr[8], pi[8];                     // R^(2^i)
+  double pr[6], pi[6];                     // R^(2^i)
   pr[0] = cd; pi[0] = sd;
 #pragma unroll
-  for (int i = 1; i < 8; i++) { pr[i] = pr[i - 1] * pr[i - 1] - pi[i - 1] * pi[i - 1]; pi[i] = 2.0 * pr[i - 1] * pi[i - 1]; }
+  for (int i = 1; i < 6; i++) { pr[i] = pr[i - 1] * pr[i - 1] - pi[i - 1] * pi[i - 1]; pi[i] = 2.0 * pr[i - 1] * pi[i - 1]; }
   // Z_b = R^b
   double zr0 = 1.0, zi0 = 0.0, zr1 = cd, zi1 = sd;
   const double cf = 2.0 * cd;
@@ -50,17 +50,11 @@ SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, const do
     sm.seeds[8 + 2 * b][s] = (TM)zr2; sm.seeds[9 + 2 * b][s] = (TM)zi2;
     zr0 = zr1; zi0 = zi1; zr1 = zr2; zi1 = zi2;
   }
-  // E_c = E0 * R^(16(TW-1))
-  double er = c0, ei = s0;
-#pragma unroll
-  for (int i = 4; i < 8; i++) {
-    if (!haveCentre && ((16 * (TW - 1)) & (1 << i))) { const double t = er * pr[i] - ei * pi[i]; ei = er * pi[i] + ei * pr[i]; er = t; }
-  }
   // Y_a = E_c * R^(8a)
 #pragma unroll
   for (int a = 0; a < 4; a++) {
     sm.seeds[2 * a][s] = (TM)er; sm.seeds[2 * a + 1][s] = (TM)ei;
-    const double t = er * pr[3] - ei * pi[3]; ei = er * pi[3] + ei * pr[3]; er = t;
+    if (a < 3) { const double t = er * pr[3] - ei * pi[3]; ei = er * pi[3] + ei * pr[3]; er = t; }
   }
   // Q'_pc = A_c R^(16+32p), all of them staged (measured: letting the lanes advance p with a three-term
   // recurrence from Q_0 trades broadcast loads for three-operand FP64 ops and is 6 % slower)
@@ -72,7 +66,7 @@ SRB_HD void make_seeds_pair(const Params& P, const Geom& g, double tau, const do
       sm.rec[s][C::QOFF + 2 * (p * C::NC + c)] = (TM)(V[c] * qr);
       sm.rec[s][C::QOFF + 2 * (p * C::NC + c) + 1] = (TM)(V[c] * qi);
     }
-    const double t = qr * pr[5] - qi * pi[5]; qi = qr * pi[5] + qi * pr[5]; qr = t;
+    if (p + 1 < TW / 2) { const double t = qr * pr[5] - qi * pi[5]; qi = qr * pi[5] + qi * pr[5]; qr = t; }
   }
 }
 
