@@ -142,9 +142,21 @@ int srb_integrate_host(const srb_grid* grid, const srb_tracks* tracks, double* c
 int srb_swap_axes(const double* src, double* dst, uint32_t nSnaps, uint32_t nOmega,
                   uint32_t nAxis2, uint32_t nPhi, void* stream);
 
+/* Angle-integrated energy spectrum of snapshot `iSnap`, on the device -- the integrals of utils.py:75-95
+ * (`get_energy_spectrum`) without the unit prefactors.  layout = 0: spectra in the device layout
+ * (nSnaps, nPhi, nAxis2, nOmega) as srb_integrate leaves them; layout = 1: (nSnaps, nOmega, nAxis2, nPhi) as
+ * srb_swap_axes leaves them.  val = sum_k spectra[k] (coherent != 0: sum_k spectra[k]^2, the *_complex comps);
+ *   far : out[j] = dphi * sum_phi trapz( 0.5 (val[a+1] + val[a]) * sin(th_mid[a]) ; th_mid ),  th_mid = mid-points of theta
+ *   near: out[j] = dphi * sum_phi trapz( val[a] * r[a] ; r )
+ * axis2 = theta (far) or radius (near), float64[nAxis2] on the device; out = float64[nOmega] on the device,
+ * overwritten.  Deterministic (fixed summation order). */
+int srb_energy_spectrum(int mode, int layout, const double* const* spectra, int n_spectra, int coherent,
+                        uint32_t nOmega, uint32_t nAxis2, uint32_t nPhi, uint32_t nSnaps, uint32_t iSnap,
+                        const double* axis2, double dphi, double* out, void* stream);
+
 /* How the last srb_integrate was configured (for benchmarks/diagnostics). */
 typedef struct srb_launch_info {
-  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32, 3 pair */
+  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32, 3 pair, 4 pair on the scalar pipe */
   int32_t tile_width;  /* omega nodes per thread */
   uint32_t chunk_nodes, n_chunks, n_virtual_dirs, n_particle_chunks;
   uint32_t grid_blocks, block_threads, smem_bytes;

@@ -18,7 +18,7 @@ PHASOR = {'auto': 0, 'direct': 1, 'recur': 2, 'pair': 3, 'pair_fma': 4}
 # every symbol include/synchrad_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ('srb_version', 'srb_last_error', 'srb_num_spectra', 'srb_scratch_bytes',
            'srb_integrate', 'srb_integrate_host', 'srb_swap_axes', 'srb_last_launch',
-           'srb_pipe_peak')
+           'srb_pipe_peak', 'srb_energy_spectrum')
 
 
 class srb_grid(ctypes.Structure):
@@ -91,6 +91,9 @@ def load():
     lib.srb_swap_axes.restype = ctypes.c_int
     lib.srb_swap_axes.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_uint32] * 4 \
         + [ctypes.c_void_p]
+    lib.srb_energy_spectrum.restype = ctypes.c_int
+    lib.srb_energy_spectrum.argtypes = [ctypes.c_int, ctypes.c_int, P(ctypes.c_void_p), ctypes.c_int, ctypes.c_int] \
+        + [ctypes.c_uint32] * 5 + [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
     lib.srb_pipe_peak.restype = ctypes.c_int
     lib.srb_pipe_peak.argtypes = [ctypes.c_int, P(ctypes.c_double)]
     lib.srb_last_launch.restype = ctypes.c_int

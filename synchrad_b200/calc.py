@@ -249,6 +249,8 @@ class SynchRad(Utilities):
             from .dist import reduce_to_root
             dev_out, self.total_weight, cnt = reduce_to_root(self.comm, dev_out, self.total_weight, cnt)
         self.Data['radiation'] = {k: d.cpu().numpy() for k, d in zip(keys, dev_out)}
+        # the summed result stays on the device of rank 0 for the on-device post-processing (utils.py, on_device=True)
+        self._dev_radiation = dict(zip(keys, dev_out)) if self.rank == 0 else None
         c = cnt.cpu().numpy()
         self.last_run = {
             'passed_updates': int(c[0]), 'visited_updates': int(c[1]),

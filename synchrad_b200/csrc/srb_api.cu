@@ -136,6 +136,61 @@ __global__ void k_swap_axes(const double* __restrict__ src, double* __restrict__
   }
 }
 
+// Angle integrals of utils.py:75-95 on the device: thread = (omega node, phi slice); the phi slices of a node are
+// summed through shared memory in a fixed order.
+struct SpecPtrs { const double* p[6]; };
+__global__ void k_energy_spectrum(SpecPtrs S, int nK, int coherent, int far, int layout, uint32_t nO, uint32_t nA, uint32_t nP,
+                                  uint32_t iSnap, const double* __restrict__ ax, double dphi, double* __restrict__ out) {
+  __shared__ double part[8][33];
+  const uint32_t j = blockIdx.x * 32u + threadIdx.x;
+  double acc = 0.0;
+  if (j < nO) {
+    for (uint32_t ip = threadIdx.y; ip < nP; ip += 8u) {
+      // element (iSnap, j, a, ip) in either layout
+      const size_t base = layout == 0 ? ((size_t)iSnap * nP + ip) * nA * (size_t)nO + j
+                                      : ((size_t)iSnap * nO + j) * nA * (size_t)nP + ip;
+      const size_t sA = layout == 0 ? (size_t)nO : (size_t)nP;
+      auto val = [&](uint32_t a) {
+        double v = 0.0;
+        for (int k = 0; k < nK; k++) { const double s = S.p[k][base + (size_t)a * sA]; v += coherent ? s * s : s; }
+        return v;
+      };
+      double sum = 0.0;
+      if (far) {
+        if (nA >= 3) {
+          double v0 = val(0), v1 = val(1);
+          double tm0 = 0.5 * (ax[1] + ax[0]);
+          double y0 = 0.5 * (v1 + v0) * sin(tm0);
+          for (uint32_t a = 1; a + 1 < nA; a++) {
+            const double v2 = val(a + 1);
+            const double tm1 = 0.5 * (ax[a + 1] + ax[a]);
+            const double y1 = 0.5 * (v2 + v1) * sin(tm1);
+            sum += 0.5 * (y1 + y0) * (tm1 - tm0);
+            v1 = v2; tm0 = tm1; y0 = y1;
+          }
+        }
+      } else {
+        if (nA >= 2) {
+          double y0 = val(0) * ax[0];
+          for (uint32_t a = 1; a < nA; a++) {
+            const double y1 = val(a) * ax[a];
+            sum += 0.5 * (y1 + y0) * (ax[a] - ax[a - 1]);
+            y0 = y1;
+          }
+        }
+      }
+      acc += sum;
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < nO) {
+    double t = 0.0;
+    for (int k = 0; k < 8; k++) t += part[k][threadIdx.x];
+    out[j] = dphi * t;
+  }
+}
+
 // Issue-rate micro-kernels: the denominators of the compute roofline, measured on
 // the device the benchmark runs on.  8 independent FMA chains per thread, 16 warps per SM.
 template <typename T, bool MUFU>
@@ -458,6 +513,22 @@ int srb_swap_axes(const double* src, double* dst, uint32_t nSnaps, uint32_t nO, 
   SRB_CUDA(cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, dev));
   const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)numSM * 8);
   k_swap_axes<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, nSnaps, nO, nA, nP);
+  SRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srb_energy_spectrum(int mode, int layout, const double* const* spectra, int n_spectra, int coherent, uint32_t nO, uint32_t nA,
+                        uint32_t nP, uint32_t nSnaps, uint32_t iSnap, const double* axis2, double dphi, double* out,
+                        void* stream) {
+  if (mode != SRB_MODE_FAR && mode != SRB_MODE_NEAR) return fail("srb_energy_spectrum: bad mode");
+  if (layout != 0 && layout != 1) return fail("srb_energy_spectrum: layout must be 0 (device) or 1 (swapped)");
+  if (!spectra || n_spectra < 1 || n_spectra > 6) return fail("srb_energy_spectrum: 1..6 spectra expected");
+  if (!axis2 || !out || nO == 0 || nA == 0 || nP == 0) return fail("srb_energy_spectrum: empty grid or null buffer");
+  if (iSnap >= nSnaps) return fail("srb_energy_spectrum: snapshot index out of range");
+  SpecPtrs S{};
+  for (int k = 0; k < n_spectra; k++) { if (!spectra[k]) return fail("srb_energy_spectrum: null spectrum"); S.p[k] = spectra[k]; }
+  k_energy_spectrum<<<(nO + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(S, n_spectra, coherent, mode == SRB_MODE_FAR,
+                                                                               layout, nO, nA, nP, iSnap, axis2, dphi, out);
   SRB_CUDA(cudaGetLastError());
   return 0;
 }

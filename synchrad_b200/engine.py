@@ -173,6 +173,23 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
         return res
 
 
+def energy_spectrum(mode, spectra, coherent, nSnaps, n_w, n_2, n_p, iteration, axis2, dphi, layout=1):
+    """Angle integrals of utils.py:75-95 on the device (srb_energy_spectrum): returns float64[n_w] on the device.
+    `spectra`: float64 device tensors, layout 1 = (nSnaps, n_w, n_2, n_p), 0 = (nSnaps, n_p, n_2, n_w)."""
+    lib = _lib.load()
+    dev = spectra[0].device
+    it = int(iteration) % int(nSnaps)
+    ax = torch.as_tensor(np.ascontiguousarray(axis2, dtype=np.float64), device=dev)
+    out = torch.empty(n_w, dtype=torch.float64, device=dev)
+    ptrs = (ctypes.c_void_p * len(spectra))(*[s.data_ptr() for s in spectra])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        _lib.check(lib.srb_energy_spectrum(0 if mode == 'far' else 1, int(layout), ptrs, len(spectra), int(bool(coherent)),
+                                           n_w, n_2, n_p, int(nSnaps), it, ax.data_ptr(), float(dphi), out.data_ptr(),
+                                           ctypes.c_void_p(stream.cuda_stream)))
+    return out
+
+
 def to_host_layout(spectra, nSnaps, n_w, n_2, n_p):
     """Device-side `swapaxes(-1,-3)` (calc.py:573-577): (nSnaps,nPhi,nA2,nOmega) ->
     contiguous (nSnaps,nOmega,nA2,nPhi), still on the device."""

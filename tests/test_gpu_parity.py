@@ -161,6 +161,35 @@ def test_pair_kernel_tensor_core_path_forced(cuda_lib, oracle):
                                                  it_range=(0, 1500))['radiation'])
 
 
+def test_on_device_energy_spectrum_matches_host_integrals(cuda_lib):
+    """the angle integrals of utils.py:75-95 evaluated on the GPU (srb_energy_spectrum, both spectrum
+    layouts) against the NumPy path on the downloaded spectrum: far/near, incoherent/coherent comps, snapshots."""
+    import torch
+    from synchrad_b200 import engine
+    tracks, dt, info = cases.undulator_tracks(3, seed=2)
+    for near, comp, grid in ((False, 'total', (96, 9, 5)), (False, 'cartesian_complex', (70, 7, 6)),
+                             (False, 'spheric', (40, 2, 3)), (True, 'cartesian', (48, 11, 4))):
+        args = cases.undulator_args(info, near=near, grid=grid)
+        kw = dict(L_screen=1e5) if near else {}
+        calc = run_gpu(args, tracks, dt, comp=comp, nSnaps=3, **kw)
+        for it in (-1, 0, 1):
+            host_spec = calc.get_energy_spectrum(lambda0_um=0.8, iteration=it)
+            dev_spec = calc.get_energy_spectrum(lambda0_um=0.8, iteration=it, on_device=True)
+            np.testing.assert_allclose(dev_spec, host_spec, rtol=1e-12, atol=1e-14 * np.abs(host_spec).max())
+        e_host, e_dev = calc.get_energy(phot_num=True), calc.get_energy(phot_num=True, on_device=True)
+        assert abs(e_dev - e_host) <= 1e-12 * abs(e_host)
+        # layout 0 = the layout srb_integrate leaves on the device
+        n_w, n_2, n_p = grid
+        dev_layout = [torch.as_tensor(np.ascontiguousarray(v.swapaxes(-1, -3)), device='cuda:0')
+                      for v in calc.Data['radiation'].values()]
+        a = engine.energy_spectrum(calc.Args['mode'], dev_layout, comp.endswith('complex'), 3, n_w, n_2, n_p, -1,
+                                   calc.Args['radius'] if near else calc.Args['theta'], float(calc.Args['dph']), layout=0)
+        b = engine.energy_spectrum(calc.Args['mode'], list(calc._dev_radiation.values()), comp.endswith('complex'), 3,
+                                   n_w, n_2, n_p, -1, calc.Args['radius'] if near else calc.Args['theta'],
+                                   float(calc.Args['dph']), layout=1)
+        assert torch.equal(a, b)
+
+
 # ---------------------------------------------------------------------------- golden fixtures
 def test_golden_small_cases(cuda_lib):
     import golden.make_golden as mg
