@@ -1,0 +1,107 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+Runs the UNMODIFIED reference (`/root/reference/synchrad`: calc.py, utils.py, kernel_*.cl) in this image.
+The reference needs pyopencl, mako and h5py, none of which is installed; `oracle/clshim/` provides stand-ins
+that compile the reference's own kernel sources for the host (see clshim/pyopencl/__init__.py).  Everything
+else -- argument handling, axes, tables, the per-particle launch loop, snapshots, the axis swap, the HDF5
+writer calls, utils.py post-processing -- is the reference's code, imported from where it lies.
+
+Because the repo ships its own `synchrad` alias package, the reference is imported in a separate process whose
+sys.path has /root/reference first and the repo root absent:
+
+    from oracle import run_reference
+    res = run_reference.run(args, tracks, timeStep=dt, comp='total', ...)        # -> dict like reference_path's
+
+/root/reference does not exist on the GPU box: only tests/golden/make_reference_golden.py (run here, output
+committed) and the `not gpu` tests (skipped when the reference is absent) call this.
+"""
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+
+REFERENCE_ROOT = os.environ.get('SYNCHRAD_REFERENCE', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+
+
+def available():
+    return os.path.exists(os.path.join(REFERENCE_ROOT, 'synchrad', 'calc.py'))
+
+
+def run(args, tracks=None, cxxflags=None, threads=None, post=(), **kw):
+    """One `SynchRad(args).calculate_spectrum(tracks, **kw)` of the reference.  `post`: names of Utilities
+    methods to evaluate afterwards, each as (method, kwargs).  Returns dict(radiation, total_weight, Args,
+    snap_iterations, post)."""
+    if not available():
+        raise RuntimeError(f'reference not found under {REFERENCE_ROOT}')
+    with tempfile.TemporaryDirectory() as tmp:
+        req, out = os.path.join(tmp, 'req.pkl'), os.path.join(tmp, 'out.pkl')
+        with open(req, 'wb') as f:
+            pickle.dump(dict(args=args, tracks=tracks, kw=kw, post=list(post)), f)
+        env = dict(os.environ)
+        env.pop('PYTHONPATH', None)
+        if cxxflags is not None:
+            env['CLSHIM_CXXFLAGS'] = cxxflags
+        if threads is not None:
+            env['OMP_NUM_THREADS'] = str(threads)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), req, out], env=env, cwd=tmp,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('reference run failed:\n' + r.stdout[-2000:] + r.stderr[-4000:])
+        with open(out, 'rb') as f:
+            res = pickle.load(f)
+        res['log'] = r.stdout
+        return res
+
+
+def _intern(v):
+    """calc.py compares option strings with `is`; literals are interned, unpickled strings are not."""
+    if isinstance(v, str):
+        return sys.intern(v)
+    if isinstance(v, dict):
+        return {_intern(k): _intern(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_intern(x) for x in v]
+    if isinstance(v, tuple):
+        return tuple(_intern(x) for x in v)
+    return v
+
+
+def _child(req_path, out_path):
+    import warnings
+    warnings.filterwarnings('ignore', category=SyntaxWarning)
+    bad = {os.path.abspath(p or os.getcwd()) for p in (_REPO, _HERE)}
+    sys.path[:] = [REFERENCE_ROOT] + [p for p in sys.path if os.path.abspath(p or os.getcwd()) not in bad] \
+        + [os.path.join(_HERE, 'clshim')]            # appended: real pyopencl/mako/h5py win when installed
+    import numpy as np
+    with open(req_path, 'rb') as f:
+        req = _intern(pickle.load(f))
+    from synchrad.calc import SynchRad
+    import synchrad
+    assert os.path.abspath(synchrad.__path__[0]).startswith(os.path.abspath(REFERENCE_ROOT)), synchrad.__path__
+    args = dict(req['args'])
+    args.setdefault('ctx', [0, 0])
+    calc = SynchRad(args)
+    kw = dict(req['kw'])
+    kw.setdefault('verbose', False)
+    tracks = req['tracks']
+    if tracks is not None:
+        tracks = [list(t) for t in tracks]
+        calc.calculate_spectrum(particleTracks=tracks, **kw)
+    else:
+        calc.calculate_spectrum(**kw)
+    snaps = calc.snap_iterations.get() if hasattr(calc.snap_iterations, 'get') else calc.snap_iterations
+    keep = {k: v for k, v in calc.Args.items() if k not in ('grid', 'ctx')}
+    post = {}
+    for i, (meth, pkw) in enumerate(req['post']):
+        post[i] = np.asarray(getattr(calc, meth)(**pkw))
+    with open(out_path, 'wb') as f:
+        pickle.dump(dict(radiation=calc.Data['radiation'], total_weight=float(calc.total_weight), Args=keep,
+                         snap_iterations=np.asarray(snaps), post=post,
+                         device=f'{calc.dev_type} {calc.dev_name} / {calc.ocl_version}'), f)
+
+
+if __name__ == '__main__':
+    _child(sys.argv[1], sys.argv[2])
