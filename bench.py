@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype double|float] [--phasor auto|direct|recur|pair|pair_fma]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
+    python bench.py --impl reference ...      # the reference's kernels compiled for the host cores (oracle/_ref)
 
 Workload (config.workload): BASELINE.json configs[4] "synthetic PIC-scale tracks 10^5 particles x
 10^4 steps, 256x32x32 grid, sharded over 8 GPUs" — each GPU integrates its shard of 12 500
@@ -81,12 +81,27 @@ class ClockSampler:
                 'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def cpu_arm():
+    """('reference', 'ref_fast') when oracle/_ref holds the reference's own kernels compiled for the host
+    (oracle/ref_kernels.py, built where /root/reference exists and shipped with the snapshot), else the
+    oracle port ('port', 'fast')."""
+    from oracle import ref_kernels
+    return ('reference', 'ref_fast') if ref_kernels.available('fast') else ('port', 'fast')
+
+
+CPU_ARM_TEXT = {'reference': "the reference's own kernel_farfield.cl compiled for the host cores (oracle/_ref: g++ -O3 "
+                             "-march=x86-64-v3 -ffp-contract=fast, OpenMP over work-items), one launch per particle as calc.py does",
+                'port': 'oracle fast build (restated kernels, -O3 AVX2 OpenMP), one call per particle'}
+
+
 def cpu_port_rate(n_particles, n_steps, threads=None):
-    """Times the oracle's fast build (the restated reference algorithm, OpenMP over grid nodes,
-    one particle per call as the reference launches) on a bounded sample of the workload."""
+    """Times the reference's kernels on the host cores (oracle/_ref; the oracle's fast build of the restated
+    kernels when oracle/_ref is absent), OpenMP over grid nodes, one particle per launch as the reference
+    launches, on a bounded sample of the workload."""
     from oracle import reference_path as rp
     from synchrad_b200 import synthetic
     rp.build()
+    lib = cpu_arm()[1]
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (libgomp reads the
     # variable when the oracle library is first loaded)
     os.environ['OMP_NUM_THREADS'] = str(threads or os.cpu_count())
@@ -96,18 +111,20 @@ def cpu_port_rate(n_particles, n_steps, threads=None):
     args = synthetic.c5_args(GRID)
     args['ctx'] = False
     t0 = time.perf_counter()
-    res = rp.calculate_spectrum(args, tracks, synthetic.C5_DT, lib='fast')
+    res = rp.calculate_spectrum(args, tracks, synthetic.C5_DT, lib=lib)
     dt = time.perf_counter() - t0
     return res['updates'] / dt, res['updates'], dt
 
 
 def run_reference(a):
-    """--impl reference: the reference's own algorithm on the host cores.  The reference's OpenCL
-    path cannot run here (no pyopencl/pocl and nothing gcc can compile in /root/reference), so this
-    is the oracle port (oracle/oracle_kernels.cpp, -O3 AVX2 OpenMP), one particle per call."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores: its OpenCL C
+    kernels compiled for the host (oracle/_ref, see oracle/ref_kernels.py; there is no OpenCL runtime in the
+    image) behind the per-particle launch loop of calc.py as restated in oracle/reference_path.py.  Falls back
+    to the oracle port (oracle/oracle_kernels.cpp, -O3 AVX2 OpenMP) only when oracle/_ref is absent."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
     cores = os.cpu_count()
+    kind = cpu_arm()[0]
     n_steps = a.track_steps
     times, upd = [], 0
     for i in range(a.warmup + a.steps):
@@ -116,7 +133,8 @@ def run_reference(a):
             times.append(dt); upd += u
     tot = sum(times)
     val = upd / tot
-    sample = f'{a.ref_particles} particle(s) x {n_steps} samples x {GRID[0]}x{GRID[1]}x{GRID[2]} nodes per step'
+    sample = (f'{a.ref_particles} particle(s) x {n_steps} samples x {GRID[0]}x{GRID[1]}x{GRID[2]} nodes per step; '
+              + CPU_ARM_TEXT[kind])
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'updates/s', 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': 1e3 * tot / max(a.steps, 1),
@@ -124,7 +142,7 @@ def run_reference(a):
         'data': 'synthetic',
         'config': {'workload': 'C5 shard recipe (synthetic PIC-scale tracks, 256x32x32 grid, far, total), '
                                'bounded sample: ' + sample, 'grid': list(GRID), 'track_steps': n_steps},
-        'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -252,9 +270,9 @@ def run_product(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, upd, dt = cpu_port_rate(a.cpu_particles, n_s)
-        cpu = {'value': rate, 'unit': 'updates/s', 'cores': os.cpu_count(), 'kind': 'port',
+        cpu = {'value': rate, 'unit': 'updates/s', 'cores': os.cpu_count(), 'kind': cpu_arm()[0],
                'sample': f'{a.cpu_particles} particle(s) x {n_s} samples x {GRID[0]}x{GRID[1]}x{GRID[2]} nodes '
-                         f'({upd:.3g} updates, {dt:.1f} s) of the same synthetic recipe; oracle fast build'}
+                         f'({upd:.3g} updates, {dt:.1f} s) of the same synthetic recipe; ' + CPU_ARM_TEXT[cpu_arm()[0]]}
     if world > 1:
         dist.barrier()
     if rank != 0:

@@ -186,7 +186,13 @@ def calculate_spectrum(Args, particleTracks, timeStep, comp='total', L_screen=No
     Np = len(particleTracks)
     if Np_max is not None:
         Np = min(Np_max, Np)
-    lib_ = _lib(lib)
+    ref_prog = None
+    if lib in ('ref_strict', 'ref_fast'):       # the reference's own kernels from oracle/_ref (ref_kernels.py)
+        from . import ref_kernels
+        assert ct != 2, 'no long-double build of the reference kernels'
+        ref_prog = ref_kernels.load(A['mode'], A['dtype'], lib[4:])
+    else:
+        lib_ = _lib(lib)
     total = {k: np.zeros((nSnaps, No, N2, Nphi)) for k in keys}
     total_weight = 0.0
     passed = ctypes.c_longlong(0)
@@ -215,6 +221,12 @@ def calculate_spectrum(Args, particleTracks, timeStep, comp='total', L_screen=No
                 snaps = snap_iterations(rng, nSnaps)
             else:
                 rng = it_range
+            if ref_prog is not None:
+                ref_kernels.process_track(ref_prog, A['mode'], comp, spectra, arrs, t[6], it_start, rng[-1], D,
+                                          A['L_screen'] if near else None, A['gridNodeNums'], A['timeStep'], nSnaps,
+                                          snaps, ff, dtype)
+                updates += max(0, min(n - 1, int(rng[-1]) - 1)) * A['numGridNodes']
+                continue
             rc = lib_.srb_oracle_particle(
                 1 if near else 0, COMP_CODES[comp], ct, sp_ptrs,
                 *[_ptr(a) for a in arrs], float(dtype(t[6])), int(it_start), int(rng[-1]), n,
@@ -227,7 +239,7 @@ def calculate_spectrum(Args, particleTracks, timeStep, comp='total', L_screen=No
             updates += max(0, min(n - 1, int(rng[-1]) - 1)) * A['numGridNodes']
         for k, s in zip(keys, spectra):               # calc.py:573-577 then :560-571
             total[k] += np.ascontiguousarray(s.swapaxes(-1, -3), dtype=np.double)
-    return dict(radiation=total, total_weight=total_weight, Args=A, passed=passed.value,
+    return dict(radiation=total, total_weight=total_weight, Args=A, passed=None if ref_prog is not None else passed.value,
                 updates=updates, snap_iterations=snaps)
 
 

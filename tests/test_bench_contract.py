@@ -24,7 +24,11 @@ def test_reference_arm_json_line():
     assert d['impl'] == 'reference' and d['unit'] == 'updates/s' and d['higher_is_better'] is True
     assert d['n_gpus'] == 2 and d['steps'] == 1 and d['warmup'] == 0 and d['scaling'] == 'weak'
     assert d['value'] > 1e6 and d['vs_baseline'] is None and d['data'] == 'synthetic'
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] == os.cpu_count()
+    sys.path.insert(0, ROOT)
+    from oracle import ref_kernels
+    # 'reference' = the reference's own kernels compiled for the host (oracle/_ref), 'port' only when absent
+    assert d['cpu_baseline']['kind'] == ('reference' if ref_kernels.available('fast') else 'port')
+    assert d['cpu_baseline']['cores'] == os.cpu_count()
     assert d['cpu_baseline']['value'] == d['value'] == d['e2e']['value']
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config'] and d['gpu_launches'] == 0

@@ -184,3 +184,44 @@ def test_pyopencl_stand_in_rejects_what_pyopencl_rejects():
         prog.scale(q, (8,), (8,), arr.to_device(q, np.arange(5, dtype=np.float32)).data, np.double(2.0), np.uint32(5))
     with pytest.raises(ValueError):
         prog.scale(q, (9,), (8,), x.data, np.double(2.0), np.uint32(5))   # global size not a multiple of local
+
+
+# ------------------------------------------------------------------------------- oracle/_ref (compiled reference kernels)
+def test_compiled_reference_kernels_equal_the_stored_vectors(oracle, ref_gold):
+    """oracle/_ref holds the reference's kernels compiled ahead of time (oracle/ref_kernels.py); the strict
+    build behind the oracle's launch loop must give the stored reference outputs bit for bit, and the fast build
+    (FMA contraction on -- what bench.py times as the CPU baseline) must stay within the spread documented in
+    DESIGN.md §5 on a benign case."""
+    from oracle import ref_kernels
+    if not ref_kernels.available('strict'):
+        pytest.skip('oracle/_ref not built (no /root/reference at build time)')
+    stored, _ = ref_gold
+    for name in ('far_cartesian_snaps', 'near_cartesian_complex', 'float_near_total', 'far_spheric_complex'):
+        args, tracks, dt, kw = ALL[name]
+        res = oracle.calculate_spectrum(args, tracks, dt, lib='ref_strict', **kw)
+        for key, arr in res['radiation'].items():
+            assert np.array_equal(arr, stored[f'{name}/{key}']), (name, key)
+    args, tracks, dt, kw = ALL['c5_small']
+    fast = oracle.calculate_spectrum(args, tracks, dt, lib='ref_fast', **kw)['radiation']['total']
+    assert max(rel_errors(fast, stored['c5_small/total'])) < 1e-10
+
+
+# ------------------------------------------------------------------------------- the product's host-side mirror
+@pytest.mark.parametrize('name', ['far_total', 'far_cartesian_complex', 'far_spheric', 'near_total',
+                                  'near_cartesian_complex', 'opt_snaps_per_track_range', 'opt_single_node_axes',
+                                  'opt_weights_mean', 'wiggler_wavelengthgrid'])
+def test_product_utilities_match_reference_utils(ref_gold, name):
+    """synchrad_b200.utils (the product's mirror of utils.py:23-102) applied to the reference's stored spectra
+    against what the reference's own utils.py returned for them (no device needed: ctx=False)."""
+    from synchrad.calc import SynchRad
+    stored, meta = ref_gold
+    args, tracks, dt, kw = ALL[name]
+    a = dict(args)
+    a['ctx'] = False
+    calc = SynchRad(a)
+    calc.Data['radiation'] = {k: stored[f'{name}/{k}'] for k in meta[name]['keys']}
+    calc.Args['comp'] = kw.get('comp', 'total')
+    calc.total_weight = meta[name]['total_weight']
+    for i, (meth, pkw) in enumerate(POST):
+        np.testing.assert_allclose(getattr(calc, meth)(**pkw), stored[f'{name}/post{i}'], rtol=1e-13, atol=0,
+                                   err_msg=f'{name} {meth} {pkw}')
