@@ -20,13 +20,15 @@
 // implementation-defined, so the reference has no single bit-exact answer;
 // this file fixes one.
 //
-// PARITY PIN: the reference stores no golden vectors and its OpenCL path cannot run in this
-// image (no pyopencl / pocl).  This oracle is pinned (tests/test_oracle_golden.py) against
+// PARITY PIN: PINNED.  The reference stores no golden vectors, but its unmodified host code and kernel sources
+// run in the build container through oracle/run_reference.py (pyopencl/mako/h5py stand-ins in oracle/clshim; the
+// .cl files compiled for the host under the same arithmetic policy as above).  Its outputs on 26 cases are
+// committed as tests/golden/reference_cases.npz, and tests/test_reference_pin.py requires this oracle to equal
+// every stored array bit for bit (np.array_equal), in double and in single precision.  Further pins:
 //   (1) the reference's own known-answer criterion, the analytic undulator energy of
 //       tests/test_undulator_analytic.py:78-87 and tests/test_undulator_analytic_near.py:81-90,
-//   (2) the spot values of BASELINE.md §2 (an independent NumPy restatement made during the
-//       survey), and (3) an independent vectorised NumPy restatement in oracle/numpy_oracle.py.
-// Bit-level parity with "the" OpenCL result is therefore UNPINNED (no such result exists here).
+//   (2) the spot values of BASELINE.md §2, (3) the NumPy restatement in oracle/numpy_oracle.py.
+// What stays implementation-defined is the OpenCL driver's contraction / libm (measured spread: DESIGN.md §5).
 //
 // Compute types: 0 = double, 1 = float, 2 = long double ("truth": same double-rounded inputs,
 // 80-bit arithmetic; inputs/outputs are double arrays).

@@ -14,8 +14,10 @@ its OpenCL kernels.  Citations are file:line in /root/reference/synchrad/.
     MPI sum ..................... calc.py:560-571   (emulated by summing rank results)
     post-processing ............. utils.py:23-102   (`get_full_spectrum`/`get_energy`)
 
-Parity pin: see the header of oracle_kernels.cpp ("bit-level parity UNPINNED"; pinned to the
-reference's analytic undulator criterion and to BASELINE.md §2 spot values).
+Parity pin: PINNED -- this flow plus oracle_kernels.cpp reproduce the outputs of the unmodified reference
+(run in the build container through oracle/run_reference.py, stored in tests/golden/reference_cases.npz) bit for
+bit, in double and single precision (tests/test_reference_pin.py).  `lib='ref_strict'|'ref_fast'` drives the
+reference's own kernels from oracle/_ref (oracle/ref_kernels.py) with the same launch loop.
 """
 import ctypes
 import os

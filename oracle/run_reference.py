@@ -56,6 +56,31 @@ def run(args, tracks=None, cxxflags=None, threads=None, post=(), **kw):
         return res
 
 
+def run_many(requests, cxxflags=None, threads=None):
+    """Several runs in ONE child process: `requests` is a list of dict(args=, tracks=, kw=, post=[...]); returns
+    the list of results (an exception raised by the reference for one request is returned as
+    dict(error=repr) in its slot)."""
+    if not available():
+        raise RuntimeError(f'reference not found under {REFERENCE_ROOT}')
+    with tempfile.TemporaryDirectory() as tmp:
+        req, out = os.path.join(tmp, 'req.pkl'), os.path.join(tmp, 'out.pkl')
+        with open(req, 'wb') as f:
+            pickle.dump(dict(many=[dict(args=r['args'], tracks=r.get('tracks'), kw=r.get('kw', {}),
+                                        post=list(r.get('post', ()))) for r in requests]), f)
+        env = dict(os.environ)
+        env.pop('PYTHONPATH', None)
+        if cxxflags is not None:
+            env['CLSHIM_CXXFLAGS'] = cxxflags
+        if threads is not None:
+            env['OMP_NUM_THREADS'] = str(threads)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), req, out], env=env, cwd=tmp,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('reference run failed:\n' + r.stdout[-2000:] + r.stderr[-4000:])
+        with open(out, 'rb') as f:
+            return pickle.load(f)
+
+
 def _intern(v):
     """calc.py compares option strings with `is`; literals are interned, unpickled strings are not."""
     if isinstance(v, str):
@@ -81,26 +106,39 @@ def _child(req_path, out_path):
     from synchrad.calc import SynchRad
     import synchrad
     assert os.path.abspath(synchrad.__path__[0]).startswith(os.path.abspath(REFERENCE_ROOT)), synchrad.__path__
-    args = dict(req['args'])
-    args.setdefault('ctx', [0, 0])
-    calc = SynchRad(args)
-    kw = dict(req['kw'])
-    kw.setdefault('verbose', False)
-    tracks = req['tracks']
-    if tracks is not None:
-        tracks = [list(t) for t in tracks]
-        calc.calculate_spectrum(particleTracks=tracks, **kw)
+
+    def one(req):
+        args = dict(req['args'])
+        args.setdefault('ctx', [0, 0])
+        calc = SynchRad(args)
+        kw = dict(req['kw'])
+        kw.setdefault('verbose', False)
+        tracks = req['tracks']
+        if tracks is not None:
+            tracks = [list(t) for t in tracks]
+            calc.calculate_spectrum(particleTracks=tracks, **kw)
+        else:
+            calc.calculate_spectrum(**kw)
+        snaps = calc.snap_iterations.get() if hasattr(calc.snap_iterations, 'get') else calc.snap_iterations
+        keep = {k: v for k, v in calc.Args.items() if k not in ('grid', 'ctx')}
+        post = {}
+        for i, (meth, pkw) in enumerate(req['post']):
+            post[i] = np.asarray(getattr(calc, meth)(**pkw))
+        return dict(radiation=calc.Data['radiation'], total_weight=float(calc.total_weight), Args=keep,
+                    snap_iterations=np.asarray(snaps), post=post,
+                    device=f'{calc.dev_type} {calc.dev_name} / {calc.ocl_version}')
+
+    if 'many' in req:
+        res = []
+        for r in req['many']:
+            try:
+                res.append(one(r))
+            except Exception as exc:                      # reported per request, like the reference would raise
+                res.append(dict(error=f'{type(exc).__name__}: {exc}'))
     else:
-        calc.calculate_spectrum(**kw)
-    snaps = calc.snap_iterations.get() if hasattr(calc.snap_iterations, 'get') else calc.snap_iterations
-    keep = {k: v for k, v in calc.Args.items() if k not in ('grid', 'ctx')}
-    post = {}
-    for i, (meth, pkw) in enumerate(req['post']):
-        post[i] = np.asarray(getattr(calc, meth)(**pkw))
+        res = one(req)
     with open(out_path, 'wb') as f:
-        pickle.dump(dict(radiation=calc.Data['radiation'], total_weight=float(calc.total_weight), Args=keep,
-                         snap_iterations=np.asarray(snaps), post=post,
-                         device=f'{calc.dev_type} {calc.dev_name} / {calc.ocl_version}'), f)
+        pickle.dump(res, f)
 
 
 if __name__ == '__main__':

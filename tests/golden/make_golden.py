@@ -1,8 +1,9 @@
 """Generates tests/golden/small_cases.npz from the strict CPU oracle (run here, committed).
 
-The reference itself cannot run in this image (no pyopencl/pocl), so these vectors
-are ORACLE outputs, pinned as described in oracle/oracle_kernels.cpp; they let the GPU parity
-tests run against stored arrays as well as against a live oracle.
+These vectors are ORACLE outputs (the oracle is pinned bit for bit to the reference, see
+make_reference_golden.py / tests/test_reference_pin.py, whose reference_cases.npz holds the same cases
+produced by the unmodified reference); they let the GPU parity tests run against stored arrays as well as
+against a live oracle.
     python tests/golden/make_golden.py
 """
 import os
