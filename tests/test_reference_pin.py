@@ -225,3 +225,26 @@ def test_product_utilities_match_reference_utils(ref_gold, name):
     for i, (meth, pkw) in enumerate(POST):
         np.testing.assert_allclose(getattr(calc, meth)(**pkw), stored[f'{name}/post{i}'], rtol=1e-13, atol=0,
                                    err_msg=f'{name} {meth} {pkw}')
+
+
+@needs_reference
+@pytest.mark.parametrize('seed', [100, 101])
+def test_random_problems_oracle_equals_live_reference(oracle, seed):
+    """Differential fuzz of the oracle against the live reference (ragged tracks, it_start, ranges, snapshots,
+    every comp, near/far, log / wavelength grids, guard-dominated omega ranges): bit-identical, or both raise."""
+    import contextlib
+    import io
+    import fuzzcases
+    rs = np.random.RandomState(seed)
+    probs = [fuzzcases.rand_case(rs) for _ in range(25)]
+    outs = run_reference.run_many([dict(args=A, tracks=tr, kw=dict(kw, timeStep=dt)) for A, tr, dt, kw in probs])
+    for i, ((A, tr, dt, kw), ref) in enumerate(zip(probs, outs)):
+        if 'error' in ref:
+            with pytest.raises(Exception):
+                oracle.calculate_spectrum(A, tr, dt, **kw)
+            continue
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = oracle.calculate_spectrum(A, tr, dt, **kw)
+        for key, arr in ref['radiation'].items():
+            assert np.array_equal(res['radiation'][key], arr), (seed, i, key, A['grid'], A.get('mode'), kw)
+        assert res['total_weight'] == ref['total_weight']
