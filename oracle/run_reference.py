@@ -123,7 +123,8 @@ def _child(req_path, out_path):
         keep = {k: v for k, v in calc.Args.items() if k not in ('grid', 'ctx')}
         post = {}
         for i, (meth, pkw) in enumerate(req['post']):
-            post[i] = np.asarray(getattr(calc, meth)(**pkw))
+            r = getattr(calc, meth)(**pkw)
+            post[i] = tuple(np.asarray(x) for x in r) if isinstance(r, tuple) else np.asarray(r)
         return dict(radiation=calc.Data['radiation'], total_weight=float(calc.total_weight), Args=keep,
                     snap_iterations=np.asarray(snaps), post=post,
                     device=f'{calc.dev_type} {calc.dev_name} / {calc.ocl_version}')

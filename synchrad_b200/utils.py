@@ -1,10 +1,12 @@
 """Host-side glue the reference's analytic tests call on the finished spectrum
 (`calc.get_energy(lambda0_um=1)`, `J_in_um`; tests/test_undulator_analytic.py:4,77).
 
-Only the unit scalings and the theta/R/phi/omega integrals of /root/reference/synchrad/utils.py
-:16-19, :23-102 are provided (NumPy on a <= 50 MB array).  `on_device=True` evaluates the
-angle integrals on the GPU from the device-resident result (`srb_energy_spectrum`).
-Spot maps, VTK export and the track converters are out of scope.
+The unit scalings, the theta/R/phi/omega integrals and the spot maps of /root/reference/synchrad/utils.py
+:16-19, :23-160 are provided (NumPy on a <= 50 MB array) -- what the reference's tests and
+tutorial notebooks call on a finished calculation.  `on_device=True` evaluates the angle integrals on the GPU
+from the device-resident result (`srb_energy_spectrum`).  Every method is checked against the
+reference's own utils.py on the reference's stored spectra (tests/test_reference_pin.py).
+VTK export (needs tvtk) and the track converters are out of scope.
 """
 import numpy as np
 from scipy.constants import m_e, c, e, epsilon_0, hbar
@@ -97,6 +99,47 @@ class Utilities:
         val = self.get_energy_spectrum(spect_filter=spect_filter, phot_num=phot_num,
                                        lambda0_um=lambda0_um, on_device=on_device, **kw)
         return np.trapezoid(val, self.Args['omega'])
+
+    def get_spot(self, k0=None, spect_filter=None, phot_num=False, lambda0_um=None, **kw):
+        """Angular map (theta|R, phi): the spectrum integrated over omega, or its slice at the node closest to
+        `k0` (utils.py:104-127).  As in the reference, a single-node omega axis is weighted with `dw`, and a `k0`
+        whose nearest-from-below node is the last one raises IndexError."""
+        val = self.get_full_spectrum(spect_filter=spect_filter, phot_num=phot_num,
+                                     lambda0_um=lambda0_um, **kw)
+        omega = self.Args['omega']
+        if k0 is None:
+            if val.shape[0] > 1:
+                return np.trapezoid(val, omega, axis=0)
+            return val[0] * self.Args['dw']
+        below = int((omega < k0).sum())
+        if np.abs(omega[below + 1] - k0) < np.abs(omega[below] - k0):
+            below += 1
+        return val[below]
+
+    def get_spot_cartesian(self, k0=None, th_part=1.0, bins=(200, 200), spect_filter=None, phot_num=False,
+                           lambda0_um=None, **kw):
+        """`get_spot` resampled from the polar (theta|R, phi) nodes onto a Cartesian bins[0] x bins[1] raster of
+        half-width th_part * max(theta|R) by linear (Delaunay) interpolation, zero outside the hull
+        (utils.py:129-158).  Returns (map, [-m, m, -m, m])."""
+        from scipy.interpolate import griddata
+        spot = self.get_spot(spect_filter=spect_filter, k0=k0, phot_num=phot_num, lambda0_um=lambda0_um, **kw)
+        if self.Args['mode'] == 'far':
+            rho = self.Args['theta']
+        elif self.Args['mode'] == 'near':
+            rho = self.Args['radius']
+        else:
+            raise ValueError("get_spot_cartesian is for 'far' and 'near' modes only")
+        phi_nodes, rho_nodes = np.meshgrid(self.Args['phi'], rho)          # both (n_rho, n_phi), like the spot
+        points = ((rho_nodes * np.cos(phi_nodes)).ravel(), (rho_nodes * np.sin(phi_nodes)).ravel())
+        half = th_part * rho_nodes.max()
+        raster = np.mgrid[-half:half:bins[0] * 1j, -half:half:bins[1] * 1j]
+        out = griddata(points, spot.ravel(), (raster[0].ravel(), raster[1].ravel()), fill_value=0.,
+                       method='linear').reshape(raster[0].shape)
+        return out, np.array([-half, half, -half, half])
+
+    def exportToVTK(self, *a, **kw):
+        """utils.py:174-228 needs tvtk (mayavi); like the reference without it, report and return."""
+        print('TVTK API is not found')
 
     def get_spectral_axis(self):
         return self.Args['omega']

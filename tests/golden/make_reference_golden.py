@@ -62,6 +62,27 @@ def extra_cases():
 
 POST = [('get_energy', dict(lambda0_um=1)), ('get_energy', dict(phot_num=True)),
         ('get_energy_spectrum', dict(lambda0_um=0.8)), ('get_full_spectrum', dict(normalize_to_weights=True))]
+# spot maps (utils.py:104-158), stored as '<case>/spot<i>'; K0REL: k0 = omega_min + K0REL * (omega_max - omega_min)
+K0REL = 0.37
+POST_SPOT = [('get_spot', dict(lambda0_um=1)), ('get_spot', dict(k0=K0REL, phot_num=True)),
+             ('get_spot_cartesian', dict(bins=(24, 18), lambda0_um=1)),
+             ('get_spot_cartesian', dict(k0=K0REL, th_part=0.5, bins=(16, 16)))]
+
+
+def spot_requests(args):
+    """POST_SPOT with k0 placed inside the case's omega range (single-node axes have no k0 slice: the
+    reference indexes omega[i + 1])."""
+    lo, hi = args['grid'][0]
+    n_w = args['grid'][-1][0]
+    out = []
+    for meth, kw in POST_SPOT:
+        kw = dict(kw)
+        if 'k0' in kw:
+            if n_w < 3 or 'wavelengthGrid' in args.get('Features', ()):   # descending omega: the reference's
+                continue                                                    # index search runs off the axis
+            kw['k0'] = lo + kw['k0'] * (hi - lo)
+        out.append((meth, kw))
+    return out
 
 
 def file_flow_case(rr):
@@ -89,11 +110,18 @@ def main():
     allc = dict(small_cases())
     allc.update(extra_cases())
     for name, (args, tracks, dt, kw) in allc.items():
-        res = rr.run(args, tracks, timeStep=dt, post=POST, **kw)
+        spots = spot_requests(args) if args['grid'][-1][1] > 1 else []     # griddata needs a 2-D point set
+        res = rr.run(args, tracks, timeStep=dt, post=POST + spots, **kw)
         for key, arr in res['radiation'].items():
             blobs[f'{name}/{key}'] = arr
         for i, v in res['post'].items():
-            blobs[f'{name}/post{i}'] = v
+            if i < len(POST):
+                blobs[f'{name}/post{i}'] = v
+            elif isinstance(v, tuple):             # get_spot_cartesian returns (map, extent): keep both
+                blobs[f'{name}/spot{i - len(POST)}'] = np.asarray(v[0], dtype=np.double)
+                blobs[f'{name}/spot{i - len(POST)}_extent'] = np.asarray(v[1], dtype=np.double)
+            else:
+                blobs[f'{name}/spot{i - len(POST)}'] = v
         blobs[f'{name}/snap_iterations'] = res['snap_iterations']
         meta[name] = dict(total_weight=res['total_weight'], keys=list(res['radiation']))
         print(name, 'ok', {k: v.shape for k, v in res['radiation'].items()})
@@ -110,6 +138,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'reference_cases.npz'), **blobs)
     print('wrote', len(blobs), 'arrays')
 
+    with open(os.path.join(HERE, 'reference_cases_meta.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+    if '--cases-only' in sys.argv:
+        return
     # the reference's own test scripts (seeded): summary values of the full-size grids
     kat = {'_source': 'unmodified reference run in this container by tests/golden/make_reference_golden.py '
                       '(oracle/run_reference.py); tests/test_undulator_analytic.py and ..._near.py with '
@@ -130,8 +162,6 @@ def main():
                         deviation_percent=abs(E - Et) / Et * 100,
                         spots=[[s, float(S[tuple(s)])] for s in spots])
         print(tag, kat[tag]['energy_J'], kat[tag]['deviation_percent'])
-    with open(os.path.join(HERE, 'reference_cases_meta.json'), 'w') as f:
-        json.dump(meta, f, indent=1)
     with open(os.path.join(HERE, 'reference_kat.json'), 'w') as f:
         json.dump(kat, f, indent=1)
 

@@ -18,7 +18,7 @@ import pytest
 import cases
 from conftest import rel_errors
 from golden.make_golden import small_cases
-from golden.make_reference_golden import POST, extra_cases
+from golden.make_reference_golden import POST, extra_cases, spot_requests
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
@@ -60,6 +60,7 @@ def test_every_stored_reference_case_is_checked(ref_gold):
     stored, meta = ref_gold
     names = {k.split('/')[0] for k in stored.files}
     assert names == set(ALL) | {'file_flow'}
+    assert sum('/spot' in k for k in stored.files) > 100
     assert 'clshim' in meta['_device']
 
 
@@ -225,6 +226,15 @@ def test_product_utilities_match_reference_utils(ref_gold, name):
     for i, (meth, pkw) in enumerate(POST):
         np.testing.assert_allclose(getattr(calc, meth)(**pkw), stored[f'{name}/post{i}'], rtol=1e-13, atol=0,
                                    err_msg=f'{name} {meth} {pkw}')
+    # spot maps (utils.py:104-158): omega integral / k0 slice, and the Cartesian resampling
+    if args['grid'][-1][1] > 1:
+        for i, (meth, pkw) in enumerate(spot_requests(args)):
+            got, want = getattr(calc, meth)(**pkw), stored[f'{name}/spot{i}']
+            if isinstance(got, tuple):
+                np.testing.assert_array_equal(got[1], stored[f'{name}/spot{i}_extent'])
+                got = got[0]
+            assert got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13 * np.abs(want).max(), err_msg=f'{name} {meth} {pkw}')
 
 
 @needs_reference
@@ -248,3 +258,22 @@ def test_random_problems_oracle_equals_live_reference(oracle, seed):
         for key, arr in ref['radiation'].items():
             assert np.array_equal(res['radiation'][key], arr), (seed, i, key, A['grid'], A.get('mode'), kw)
         assert res['total_weight'] == ref['total_weight']
+
+
+def test_get_spot_quirks_follow_the_reference():
+    """utils.py:104-127: a single-node omega axis is weighted with dw; k0 above the last node runs off the axis
+    (IndexError) exactly as in the reference; the VTK export reports the missing tvtk."""
+    from synchrad.calc import SynchRad
+    calc = SynchRad({'grid': [(1.0, 2.0), (0, 0.1), (0, 2 * np.pi), (1, 3, 4)], 'ctx': False})
+    calc.Data['radiation'] = {'total': np.arange(12.0).reshape(1, 1, 3, 4)}
+    calc.Args['comp'] = 'total'
+    calc.total_weight = 1.0
+    from synchrad.utils import alpha_fs
+    np.testing.assert_allclose(calc.get_spot(), alpha_fs / (4 * np.pi ** 2) * np.arange(12.0).reshape(3, 4) * calc.Args['dw'])
+    calc5 = SynchRad({'grid': [(1.0, 2.0), (0, 0.1), (0, 2 * np.pi), (5, 3, 4)], 'ctx': False})
+    calc5.Data['radiation'] = {'total': np.ones((1, 5, 3, 4))}
+    calc5.Args['comp'] = 'total'
+    with pytest.raises(IndexError):
+        calc5.get_spot(k0=2.5)
+    assert calc5.get_spot(k0=1.26).shape == (3, 4)
+    assert calc5.exportToVTK() is None
