@@ -148,6 +148,7 @@ class SynchRad(Utilities):
             raise RuntimeError('this SynchRad object was created without a device (ctx=False)')
         from . import engine
         import torch
+        track_source = None
 
         if comp not in host.COMP_KEYS:
             raise ValueError(f'unknown comp {comp!r}')
@@ -182,7 +183,10 @@ class SynchRad(Utilities):
                 elif self.rank == 0 and verbose:
                     print('Separate it_range for each track will be used')
             index = host.select_tracks(int(n_file), Np_max, self.rank, self.size)
-            particleTracks = trackio.read_tracks(file_tracks, index)
+            # headers only: the samples go from the file straight into the pinned SoA buffers when the
+            # batches are packed below (the reference holds every local track in host RAM, calc.py:210-216)
+            track_source = trackio.TrackSource(file_tracks, index)
+            particleTracks = track_source.tracks
             if self.rank == 0 and verbose:
                 print('Tracks are loaded')
         elif isinstance(particleTracks, host.PackedTracks):
@@ -216,7 +220,7 @@ class SynchRad(Utilities):
             # Track sets larger than the device are integrated batch by batch into the same spectra
             # (the reference streams one track at a time, calc.py:257-267).  Per sample: 48 B of
             # coordinates + 48 B of pre-pass planes.
-            lengths = [np.asarray(t[0]).size for t in particleTracks]
+            lengths = [host.track_length(t) for t in particleTracks]
             budget = self.Args.get('max_batch_bytes')
             if budget is None:
                 free, _ = torch.cuda.mem_get_info(self.device)
@@ -224,18 +228,22 @@ class SynchRad(Utilities):
             spans = host.split_batches(lengths, max(int(budget) // 96, 1))
             batches = spans
         res, h2d, upd, ms = None, 0, 0, 0.0
-        for b in batches:
-            if isinstance(b, tuple):
-                alloc = engine.PinnedAlloc()
-                packed = host.pack_tracks(particleTracks[b[0]:b[1]], weights[b[0]:b[1]], np.double, it_range,
-                                          nSnaps, alloc)
-            res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
-                                   spectra=None if res is None else res.spectra,
-                                   counters_into=None if res is None else res.counters, **run)
-            h2d += int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes
-                       + packed.itStart.nbytes + packed.itEnd.nbytes + packed.itSnaps.nbytes)
-            upd += int(packed.updates_per_node)
-            ms += res.elapsed_ms
+        try:
+            for b in batches:
+                if isinstance(b, tuple):
+                    alloc = engine.PinnedAlloc()
+                    packed = host.pack_tracks(particleTracks[b[0]:b[1]], weights[b[0]:b[1]], np.double, it_range,
+                                              nSnaps, alloc)
+                res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
+                                       spectra=None if res is None else res.spectra,
+                                       counters_into=None if res is None else res.counters, **run)
+                h2d += int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes
+                           + packed.itStart.nbytes + packed.itEnd.nbytes + packed.itSnaps.nbytes)
+                upd += int(packed.updates_per_node)
+                ms += res.elapsed_ms
+        finally:
+            if track_source is not None:
+                track_source.close()
         if it_range is None and packed.n:
             self.snap_iterations = np.array(packed.itSnaps[packed.n - 1])   # last track's, as in the reference
         elif it_range is None:

@@ -27,7 +27,7 @@ class _Reader:
     def __init__(self, path):
         self.f = open(path, 'rb')
         self.base = 0
-        self._heaps, self._gheaps = {}, {}
+        self._heaps, self._gheaps, self._kids = {}, {}, {}
         self._superblock()
 
     def close(self):
@@ -118,6 +118,13 @@ class _Reader:
             self._btree_entries(child, heap_addr, out)
 
     def children(self, addr):
+        """name -> object-header address of a group's members (None if `addr` is not a group); cached, so that
+        `f['tracks/123/x']` does not re-walk the B-tree of a group with 1e5 members on every access."""
+        if addr not in self._kids:
+            self._kids[addr] = self._children(addr)
+        return self._kids[addr]
+
+    def _children(self, addr):
         for mtype, body in self.messages(addr):
             if mtype == 0x0011:
                 btree, heap = struct.unpack_from('<QQ', body, 0)
@@ -179,7 +186,8 @@ class _Reader:
             cache[key] = objs
         return cache[key][index]
 
-    def read_dataset(self, addr):
+    def dataset_info(self, addr):
+        """(numpy dtype, kind, shape, layout) of the dataset whose object header sits at `addr`."""
         dt = kind = shape = None
         layout = None
         for mtype, body in self.messages(addr):
@@ -201,6 +209,25 @@ class _Reader:
                     raise NotImplementedError('h5lite: chunked datasets are not supported')
         if dt is None or layout is None:
             raise KeyError('h5lite: object is not a dataset')
+        return dt, kind, shape, layout
+
+    def read_direct(self, addr, dest):
+        """Read a numeric dataset straight into the C-contiguous array `dest` (same element count): one
+        `readinto` from the file when the stored type is dest's, a converting copy otherwise."""
+        dt, kind, shape, layout = self.dataset_info(addr)
+        count = (int(np.prod(shape)) if len(shape) else 1) if shape is not None else 0
+        if count != dest.size:
+            raise ValueError(f'h5lite: dataset holds {count} elements, destination {dest.size}')
+        if (kind is None and dt == dest.dtype and layout[0] == 'contig' and layout[1] != UNDEF and count
+                and dest.flags.c_contiguous):
+            self.f.seek(self.base + layout[1])
+            if self.f.readinto(memoryview(dest).cast('B')) != count * dt.itemsize:
+                raise IOError('h5lite: truncated file')
+        elif count:
+            dest[...] = np.asarray(self.read_dataset(addr)).reshape(dest.shape)
+
+    def read_dataset(self, addr):
+        dt, kind, shape, layout = self.dataset_info(addr)
         if shape is None:
             return np.zeros((0,), dtype=dt)
         count = int(np.prod(shape)) if len(shape) else 1
@@ -240,6 +267,16 @@ class _RNode:
 
     def keys(self):
         return list(self._children().keys())
+
+    @property
+    def shape(self):
+        """Dataset shape, from the header only (h5py: `dset.shape`)."""
+        shape = self._rd.dataset_info(self._addr)[2]
+        return tuple(int(v) for v in shape) if shape is not None else (0,)
+
+    def read_direct(self, dest):
+        """h5py's `dset.read_direct(dest)`: fill `dest` without an intermediate array."""
+        self._rd.read_direct(self._addr, dest)
 
     def __contains__(self, name):
         try:

@@ -198,6 +198,12 @@ class PackedTracks:
                  'total', 'updates_per_node')
 
 
+def track_length(t):
+    """Samples of a track without touching its data when it is a lazy file track (trackio.FileTrack)."""
+    n = getattr(t, 'n', None)
+    return int(n) if n is not None else int(np.asarray(t[0]).size)
+
+
 def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
     """Concatenate tracks into SoA arrays of `dtype` (the product always packs float64: see
     grid_tables for why the reference's astype(float32) is not reproduced in 'float' mode).
@@ -210,7 +216,7 @@ def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
     if alloc is None:
         alloc = lambda shape, dt: np.empty(shape, dtype=dt)
     n = len(tracks)
-    lens = np.fromiter((np.asarray(t[0]).size for t in tracks), dtype=np.uint64, count=n)
+    lens = np.fromiter((track_length(t) for t in tracks), dtype=np.uint64, count=n)
     P = PackedTracks()
     P.n = n
     P.offsets = alloc((n + 1,), np.uint64)
@@ -232,7 +238,14 @@ def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
     upd = 0
     for i, t in enumerate(tracks):
         o, e = int(P.offsets[i]), int(P.offsets[i + 1])
+        direct = getattr(t, 'read_into', None)      # lazy file track: file -> packed buffer, no intermediate array
         for c in range(6):
+            if direct is not None:
+                try:
+                    direct(c, P.coords[c][o:e])
+                except ValueError as exc:
+                    raise ValueError(f'track {i}: coordinate arrays differ in length ({exc})') from None
+                continue
             a = np.asarray(t[c])
             if a.size != e - o:
                 raise ValueError(f'track {i}: coordinate arrays differ in length')

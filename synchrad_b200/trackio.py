@@ -52,6 +52,59 @@ def read_tracks(path, indices):
     return out
 
 
+class FileTrack:
+    """One track of an open tracks file, read on demand: behaves like the reference's 8-element track list
+    (`t[0..5]` coordinate arrays, `t[6]` weight, `t[7]` it_start) but holds no sample data; `read_into(c, dest)`
+    fills a slice of the packed (pinned) SoA buffer straight from the file -- SURVEY §8f-3."""
+    __slots__ = ('_g', 'n', '_w', 'it_start')
+
+    def __init__(self, group):
+        self._g = group
+        self.n = int(group['x'].shape[0]) if len(group['x'].shape) else 1
+        self._w = float(group['w'][()])
+        self.it_start = int(group['it_start'][()]) if 'it_start' in group.keys() else 0
+
+    def __len__(self):
+        return 8
+
+    def __getitem__(self, k):
+        if k < 0:
+            k += 8
+        if k < 6:
+            return np.asarray(self._g[_COMPS[k]][()], dtype=np.double)
+        if k == 6:
+            return self._w
+        if k == 7:
+            return self.it_start
+        raise IndexError(k)
+
+    def read_into(self, c, dest):
+        self._g[_COMPS[c]].read_direct(dest)
+
+
+class TrackSource:
+    """The tracks `indices` of a tracks file as FileTrack objects; keep it open until they are packed."""
+
+    def __init__(self, path, indices):
+        self._f = _h5.File(path, 'r')
+        try:
+            self.tracks = [FileTrack(self._f[f'tracks/{int(ip):d}']) for ip in indices]
+        except Exception:
+            self._f.close()
+            raise
+
+    def close(self):
+        if self._f is not None:
+            self._f.close()
+            self._f = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def write_tracks(path, tracks, cdt, it_range=None):
     """Write a tracks file in the converters' layout (converters.py:102-127)."""
     f = _h5.File(path, 'w')

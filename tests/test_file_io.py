@@ -168,3 +168,70 @@ def test_analysis_only_object_from_spectrum_file(tmp_path):
     calc = SynchRad(file_spectrum=p)
     assert calc.Args['mode'] == 'far' and calc.get_full_spectrum().shape == (6, 4, 4)
     assert calc.get_energy() > 0
+
+
+def test_lazy_file_tracks_pack_straight_from_the_file(tmp_path):
+    """`file_tracks=` goes from the file into the packed SoA buffers without per-track arrays
+    (trackio.TrackSource / FileTrack + host.pack_tracks), and gives exactly what the eager reader gives."""
+    from synchrad_b200 import host
+    rs = np.random.RandomState(3)
+    lens = [1, 2, 57, 300, 31]
+    tracks = [[rs.randn(n) for _ in range(6)] + [float(rs.uniform(0.5, 2)), int(rs.randint(0, 9))] for n in lens]
+    path = str(tmp_path / 'tracks.h5')
+    trackio.write_tracks(path, tracks, 0.02, it_range=(0, 250))
+    index = [4, 0, 2, 3]
+    eager = trackio.read_tracks(path, index)
+    with trackio.TrackSource(path, index) as src:
+        lazy = src.tracks
+        assert [host.track_length(t) for t in lazy] == [lens[i] for i in index]
+        assert [len(t) for t in lazy] == [8] * 4
+        for a, b in zip(lazy, eager):
+            assert a[6] == b[6] and a[7] == b[7] and a[-1] == b[7]
+            np.testing.assert_array_equal(a[2], b[2])
+        for it_range in (None, (0, 250)):
+            w = [t[6] for t in eager]
+            pe = host.pack_tracks(eager, w, np.double, it_range, 3)
+            pl = host.pack_tracks(lazy, w, np.double, it_range, 3)
+            assert pl.total == pe.total == sum(lens[i] for i in index)
+            for ce, cl in zip(pe.coords, pl.coords):
+                np.testing.assert_array_equal(ce, cl)
+            for name in ('offsets', 'w', 'itStart', 'itEnd', 'itSnaps'):
+                np.testing.assert_array_equal(getattr(pe, name), getattr(pl, name))
+            assert pl.updates_per_node == pe.updates_per_node
+    # a closed source cannot be read any more; a destination of the wrong size is refused
+    with trackio.TrackSource(path, [3]) as src:
+        with pytest.raises(ValueError):
+            src.tracks[0].read_into(0, np.empty(7))
+        dest = np.empty(300)
+        src.tracks[0].read_into(5, dest)
+        np.testing.assert_array_equal(dest, tracks[3][5])
+
+
+def test_read_direct_converts_other_stored_types(tmp_path):
+    path = str(tmp_path / 'f32.h5')
+    f = h5lite.File(path, 'w')
+    f['a/x'] = np.arange(10, dtype=np.float32) / 3
+    f['a/i'] = np.arange(6, dtype=np.int64).reshape(2, 3)
+    f.close()
+    f = h5lite.File(path, 'r')
+    assert f['a/x'].shape == (10,) and f['a/i'].shape == (2, 3)
+    dest = np.empty(10)
+    f['a/x'].read_direct(dest)
+    np.testing.assert_array_equal(dest, (np.arange(10, dtype=np.float32) / 3).astype(np.double))
+    di = np.empty((2, 3), dtype=np.int64)
+    f['a/i'].read_direct(di)
+    np.testing.assert_array_equal(di, np.arange(6).reshape(2, 3))
+    f.close()
+
+
+def test_group_listing_is_cached_for_many_tracks(tmp_path):
+    """Opening 2000 tracks must not re-walk the `tracks` group B-tree per access (it did: 2.7 ms per track)."""
+    import time
+    rs = np.random.RandomState(0)
+    tracks = [[rs.randn(4) for _ in range(6)] + [1.0, 0] for _ in range(2000)]
+    path = str(tmp_path / 'many.h5')
+    trackio.write_tracks(path, tracks, 0.01)
+    t0 = time.perf_counter()
+    got = trackio.read_tracks(path, range(2000))
+    assert time.perf_counter() - t0 < 5.0
+    np.testing.assert_array_equal(got[1999][3], tracks[1999][3])
