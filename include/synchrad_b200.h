@@ -66,6 +66,9 @@ extern "C" {
                                field); fp64: the accumulation over steps runs as a GEMM on the FP64 tensor cores
                                (DMMA.8x8x4) when tile width x components is a multiple of 8 */
 #define SRB_PHASOR_PAIR_FMA 4 /* the pair kernel with the accumulation kept on the scalar FP64 pipe (DFMA) */
+#define SRB_PHASOR_SPREAD 5 /* EXPERIMENTAL opt-in: all-pass steps as a type-1 non-uniform FFT (spreading onto a 2x
+                               oversampled 512-cell grid + one FFT per track; srb_spread.cuh).  Far field, fp64,
+                               total/cartesian comps, ascending uniform grids with <= 256 omega nodes; else an error */
 
 /* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
  * Tables are float64 arrays with the content `_init_data` uploads (calc.py:486-512): omega is
@@ -156,7 +159,7 @@ int srb_energy_spectrum(int mode, int layout, const double* const* spectra, int 
 
 /* How the last srb_integrate was configured (for benchmarks/diagnostics). */
 typedef struct srb_launch_info {
-  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32, 3 pair, 4 pair on the scalar pipe */
+  int32_t kind;        /* 0 direct, 1 recurrence, 2 literal fp32, 3 pair, 4 pair on the scalar pipe, 5 gridding */
   int32_t tile_width;  /* omega nodes per thread */
   uint32_t chunk_nodes, n_chunks, n_virtual_dirs, n_particle_chunks;
   uint32_t grid_blocks, block_threads, smem_bytes;

@@ -14,7 +14,8 @@ _SO = os.path.join(_HERE, 'libsrb_emu.so')
 _SRC = [os.path.join(_HERE, 'emu.cpp'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_pair.cuh'),
-        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh')]
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh'),
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_spread.cuh')]
 
 
 def build():
@@ -67,7 +68,9 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     keys = host.COMP_KEYS[comp]
     spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
     sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
-    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4}[kind]
+    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4, 'spread': 5}[kind]
+    if kind_i == 5:
+        tw = 8
     if literal:
         kind_i, tw = 0, None   # the C side switches to the literal kind; tile widths of the direct layout
     if tw is None:
