@@ -962,7 +962,9 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
           else if constexpr (C::PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else if constexpr (C::KIND == KIND_SPREAD) {
             // all-pass steps are gridded; partial / huge-phase steps go node by node into the same accumulators
+#if !defined(SRB_SPREAD_NO_MAIN)     // (tuning aid: time the prep phase alone)
             if (fullMask) main_spread<C>(P, sm, cnt, fullMask, lane, SRB_ST);
+#endif
             if (anyMask & ~fullMask) main_direct<C>(P, g, sm, cnt, 0u, anyMask & ~fullMask, lane, SRB_ST);
           }
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
