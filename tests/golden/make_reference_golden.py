@@ -123,6 +123,9 @@ def main():
             else:
                 blobs[f'{name}/spot{i - len(POST)}'] = v
         blobs[f'{name}/snap_iterations'] = res['snap_iterations']
+        for k, v in res['Args'].items():              # the reference's own Args after the call (a1, a6 of SURVEY §8)
+            if isinstance(v, (np.ndarray, np.generic, int, float)) and not isinstance(v, bool):
+                blobs[f'{name}/Args/{k}'] = np.asarray(v)
         meta[name] = dict(total_weight=res['total_weight'], keys=list(res['radiation']))
         print(name, 'ok', {k: v.shape for k, v in res['radiation'].items()})
     meta['_device'] = res['device']

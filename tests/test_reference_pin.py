@@ -277,3 +277,31 @@ def test_get_spot_quirks_follow_the_reference():
         calc5.get_spot(k0=2.5)
     assert calc5.get_spot(k0=1.26).shape == (3, 4)
     assert calc5.exportToVTK() is None
+
+
+@pytest.mark.parametrize('name', sorted(ALL))
+def test_product_args_equal_the_reference_args(ref_gold, name):
+    """the axes, spacings and volume elements the product's `host.init_args` builds -- and the
+    entries `calculate_spectrum` adds (`sigma_particle`, `timeStep`, near-field `theta`) -- against the `Args` dict of
+    the unmodified reference after the same call: same values bit for bit, same dtypes (float32 axes for
+    dtype='float', float64 spacings)."""
+    from synchrad_b200 import host
+    stored, _ = ref_gold
+    args, tracks, dt, kw = ALL[name]
+    A, dtype = host.init_args(dict(args))
+    A['sigma_particle'] = dtype(kw.get('sigma_particle', 0))
+    A['timeStep'] = dtype(dt)
+    if A['mode'] == 'near':
+        A['L_screen'] = kw['L_screen']
+        A['theta'] = np.arctan2(A['radius'], A['L_screen'])
+    ref_keys = {k.split('/')[-1] for k in stored.files if k.startswith(f'{name}/Args/')}
+    assert {'omega', 'dw', 'dV', 'phi', 'dph', 'numGridNodes', 'sigma_particle', 'timeStep'} <= ref_keys
+    for key in sorted(ref_keys):
+        want = stored[f'{name}/Args/{key}']
+        assert key in A, (name, key)
+        got = np.asarray(A[key])
+        assert got.shape == want.shape, (name, key, got.shape, want.shape)
+        np.testing.assert_array_equal(got, want, err_msg=f'{name} Args[{key}]')
+        if key in ('omega', 'theta', 'phi', 'radius', 'sigma_particle', 'timeStep', 'wavelengths'):
+            if not (key == 'theta' and A['mode'] == 'near'):
+                assert got.dtype == want.dtype, (name, key, got.dtype, want.dtype)
