@@ -109,10 +109,10 @@ def load(mode, dtype, flavour='fast'):
 
 
 def process_track(prog, mode, comp, spectra, arrs, wp, it_start, it_end, tables, L_screen, grid_nums, dt, nSnaps,
-                  snaps, form_factor, dtype, wgs=32):
-    """One kernel launch for one particle: the argument list of calc.py:292-353 (`_process_track`)."""
-    cl = _shim_pyopencl()
-    B = cl.Buffer
+                  snaps, form_factor, dtype, wgs=32, Buffer=None):
+    """One kernel launch for one particle: the argument list of calc.py:292-353 (`_process_track`).
+    `Buffer`: the buffer wrapper of the pyopencl look-alike `prog` came from (default: oracle/clshim's)."""
+    B = Buffer if Buffer is not None else _shim_pyopencl().Buffer
     n_nodes = int(np.prod(grid_nums))
     if n_nodes <= wgs:                                         # calc.py:640-646 (`_get_wgs`, CPU device: WGS = 32)
         lsz, gsz = n_nodes, n_nodes

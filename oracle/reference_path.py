@@ -188,11 +188,18 @@ def calculate_spectrum(Args, particleTracks, timeStep, comp='total', L_screen=No
     Np = len(particleTracks)
     if Np_max is not None:
         Np = min(Np_max, Np)
-    ref_prog = None
+    ref_prog, ref_buffer = None, None
     if lib in ('ref_strict', 'ref_fast'):       # the reference's own kernels from oracle/_ref (ref_kernels.py)
         from . import ref_kernels
         assert ct != 2, 'no long-double build of the reference kernels'
         ref_prog = ref_kernels.load(A['mode'], A['dtype'], lib[4:])
+    elif lib == 'compat':
+        # the PRODUCT's reference-side binding (synchrad_b200/compat: pyopencl call signature -> C ABI -> GPU) driven
+        # with the reference's own argument list, one launch per particle -- what the unmodified calc.py would do
+        from . import ref_kernels
+        from synchrad_b200.compat import pyopencl as compat_cl
+        ref_prog = compat_cl.Program(None, '', mode=A['mode'], dtype=A['dtype']).build()
+        ref_buffer = compat_cl.Buffer
     else:
         lib_ = _lib(lib)
     total = {k: np.zeros((nSnaps, No, N2, Nphi)) for k in keys}
@@ -226,7 +233,7 @@ def calculate_spectrum(Args, particleTracks, timeStep, comp='total', L_screen=No
             if ref_prog is not None:
                 ref_kernels.process_track(ref_prog, A['mode'], comp, spectra, arrs, t[6], it_start, rng[-1], D,
                                           A['L_screen'] if near else None, A['gridNodeNums'], A['timeStep'], nSnaps,
-                                          snaps, ff, dtype)
+                                          snaps, ff, dtype, Buffer=ref_buffer)
                 updates += max(0, min(n - 1, int(rng[-1]) - 1)) * A['numGridNodes']
                 continue
             rc = lib_.srb_oracle_particle(

@@ -30,7 +30,7 @@ def available():
     return os.path.exists(os.path.join(REFERENCE_ROOT, 'synchrad', 'calc.py'))
 
 
-def run(args, tracks=None, cxxflags=None, threads=None, post=(), **kw):
+def run(args, tracks=None, cxxflags=None, threads=None, post=(), backend='clshim', **kw):
     """One `SynchRad(args).calculate_spectrum(tracks, **kw)` of the reference.  `post`: names of Utilities
     methods to evaluate afterwards, each as (method, kwargs).  Returns dict(radiation, total_weight, Args,
     snap_iterations, post)."""
@@ -46,6 +46,7 @@ def run(args, tracks=None, cxxflags=None, threads=None, post=(), **kw):
             env['CLSHIM_CXXFLAGS'] = cxxflags
         if threads is not None:
             env['OMP_NUM_THREADS'] = str(threads)
+        env['SYNCHRAD_REFERENCE_BACKEND'] = backend
         r = subprocess.run([sys.executable, os.path.abspath(__file__), req, out], env=env, cwd=tmp,
                            capture_output=True, text=True)
         if r.returncode != 0:
@@ -56,7 +57,7 @@ def run(args, tracks=None, cxxflags=None, threads=None, post=(), **kw):
         return res
 
 
-def run_many(requests, cxxflags=None, threads=None):
+def run_many(requests, cxxflags=None, threads=None, backend='clshim'):
     """Several runs in ONE child process: `requests` is a list of dict(args=, tracks=, kw=, post=[...]); returns
     the list of results (an exception raised by the reference for one request is returned as
     dict(error=repr) in its slot)."""
@@ -73,6 +74,7 @@ def run_many(requests, cxxflags=None, threads=None):
             env['CLSHIM_CXXFLAGS'] = cxxflags
         if threads is not None:
             env['OMP_NUM_THREADS'] = str(threads)
+        env['SYNCHRAD_REFERENCE_BACKEND'] = backend
         r = subprocess.run([sys.executable, os.path.abspath(__file__), req, out], env=env, cwd=tmp,
                            capture_output=True, text=True)
         if r.returncode != 0:
@@ -98,8 +100,30 @@ def _child(req_path, out_path):
     import warnings
     warnings.filterwarnings('ignore', category=SyntaxWarning)
     bad = {os.path.abspath(p or os.getcwd()) for p in (_REPO, _HERE)}
+    backend = os.environ.get('SYNCHRAD_REFERENCE_BACKEND', 'clshim')
     sys.path[:] = [REFERENCE_ROOT] + [p for p in sys.path if os.path.abspath(p or os.getcwd()) not in bad] \
         + [os.path.join(_HERE, 'clshim')]            # appended: real pyopencl/mako/h5py win when installed
+    if backend == 'compat_emu':
+        # the product's reference-side binding (synchrad_b200/compat: pyopencl facade over the C ABI) under the
+        # unmodified reference, with the CPU emulation of the kernels (tests/emu) standing in for
+        # srb_integrate_host -- checks the binding's marshalling in a container without a GPU.  /root/reference
+        # stays first (the repo's `synchrad` alias must not shadow it), the repo root last (synchrad_b200 imports).
+        sys.path.insert(1, os.path.join(_REPO, 'synchrad_b200', 'compat'))
+        sys.path.append(_REPO)
+        import ctypes
+        import pyopencl
+        assert 'compat' in pyopencl.__file__, pyopencl.__file__
+        emu = ctypes.CDLL(os.path.join(_REPO, 'tests', 'emu', 'libsrb_emu.so'))
+        emu.srb_emu_integrate.restype = ctypes.c_int
+
+        def emu_integrate_host(grid, tracks, spectra_ptrs, n_spectra, device):
+            tw = next((o for o in (2, 4, 8) if 32 * o >= grid.nOmega), 8)
+            cnt = (ctypes.c_ulonglong * 2)(0, 0)
+            rc = emu.srb_emu_integrate(ctypes.byref(grid), ctypes.byref(tracks), spectra_ptrs, n_spectra, 0, tw,
+                                       ctypes.c_uint32(1), cnt, ctypes.c_int(1))
+            if rc != 0:
+                raise RuntimeError('emulator has no such configuration')
+        pyopencl._integrate_host = emu_integrate_host
     import numpy as np
     with open(req_path, 'rb') as f:
         req = _intern(pickle.load(f))
