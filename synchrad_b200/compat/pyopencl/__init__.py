@@ -84,7 +84,9 @@ class _Kernel:
         P = self.program
         n_sp = _N_SPECTRA[self.comp]
         far = P.mode == 'far'
-        n_expected = n_sp + 10 + (5 if far else 5) + 3 + 3 + (1 if self.comp.endswith('complex') else 0)
+        # spectra + (6 track arrays, wp, itStart, itEnd, nSteps) + 5 axis arguments (far: omega, sin/cos theta, sin/cos
+        # phi; near: omega, radius, sin/cos phi, L) + 3 node counts + (dt, nSnaps, itSnaps) [+ FormFactor]
+        n_expected = n_sp + 10 + 5 + 3 + 3 + (1 if self.comp.endswith('complex') else 0)
         if len(args) != n_expected:
             raise TypeError(f'{self.name}: {n_expected} kernel arguments expected, {len(args)} given')
         a = list(args)
