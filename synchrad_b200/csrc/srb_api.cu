@@ -465,6 +465,9 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
     static std::once_flag once;
     std::call_once(once, [] { srb::spread_build_tables(hostTab); });
     SRB_CUDA(cudaMemcpyToSymbolAsync(g_spread_tab, hostTab, sizeof hostTab, 0, cudaMemcpyHostToDevice, stream));
+#if defined(SRB_SPREAD_V2)
+    SRB_CUDA(cudaMemcpyToSymbolAsync(srb::c_spread_coef, hostTab + srb::SP_TAB_COEF, sizeof(double) * (srb::SP_DEG + 1) * 16, 0, cudaMemcpyHostToDevice, stream));
+#endif
     void* addr = nullptr;
     SRB_CUDA(cudaGetSymbolAddress(&addr, g_spread_tab));
     P.spreadTab = (const double*)addr;

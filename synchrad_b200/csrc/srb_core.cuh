@@ -272,6 +272,9 @@ template <bool ON> struct SpreadSmem {};
 template <> struct alignas(16) SpreadSmem<true> {   // 16-byte alignment: 128-bit shared-memory loads of the step records
   double grid[SP_N][4];                 // per cell: Re, Im of the two transverse components
   double coef[SP_DEG + 1][16];          // [power][piece]
+#if defined(SRB_SPREAD_V2)
+  double kv[SUB][SP_W + 1];             // kernel values of every step's 13 cells, written by the prep phase (lane = step)
+#endif
 };
 template <bool ON> struct SpreadState {};
 template <> struct SpreadState<true> {

@@ -30,6 +30,11 @@ constexpr int SP_TAB_DECONV = (SP_DEG + 1) * 16;            // [256]: 1 / Psi(2 
 constexpr int SP_TAB_TWID = SP_TAB_DECONV + 256;            // [256][2]: exp(+2 pi i q / SP_N)
 constexpr int SP_TAB_SIZE = SP_TAB_TWID + 512;
 constexpr double SP_BETA = 2.30 * SP_W;
+#if defined(SRB_SPREAD_V2) && defined(__CUDACC__)
+// SRB_SPREAD_V2 (NOT the shipped configuration; see the end of this file): the polynomial pieces as constant-bank
+// operands of the prep phase's DFMAs (uploaded next to g_spread_tab by srb_integrate)
+__constant__ double c_spread_coef[(SP_DEG + 1) * 16];
+#endif
 constexpr int SP_Y = 4, SP_C = 8;   // rec row of an all-pass step: [V0, V1, tau, -, y, y^2, y^4, y^8, c0re, c0im, c1re, c1im]
 
 // Host: the three tables (kernel pieces as centred monomials in y = 2t - 1, deconvolution factors, twiddles).
@@ -98,6 +103,26 @@ SRB_HD int spread_stage(const Params& P, const Geom& g, double tau, const double
   const double y = 2.0 * t - 1.0, y2 = y * y, y4 = y2 * y2;
   // 16-byte aligned groups so that the main phase reads a step with four 128-bit broadcast loads
   sm.rec[s][SP_Y] = y; sm.rec[s][SP_Y + 1] = y2; sm.rec[s][SP_Y + 2] = y4; sm.rec[s][SP_Y + 3] = y4 * y4;
+#if defined(SRB_SPREAD_V2)
+  {
+    // lane = step: all 13 kernel values of this step, 13 independent Estrin chains with warp-uniform coefficients
+    const double y8 = y4 * y4;
+#if defined(__CUDA_ARCH__)
+    const double* cf = c_spread_coef;
+#else
+    const double* cf = P.spreadTab + SP_TAB_COEF;
+#endif
+#pragma unroll
+    for (int p = 0; p < SP_W; p++) {
+      const double a0 = fma(cf[1 * 16 + p], y, cf[0 * 16 + p]), a1 = fma(cf[3 * 16 + p], y, cf[2 * 16 + p]);
+      const double a2 = fma(cf[5 * 16 + p], y, cf[4 * 16 + p]), a3 = fma(cf[7 * 16 + p], y, cf[6 * 16 + p]);
+      const double a4 = fma(cf[9 * 16 + p], y, cf[8 * 16 + p]), a5 = fma(cf[11 * 16 + p], y, cf[10 * 16 + p]);
+      const double b0 = fma(a1, y2, a0), b1 = fma(a3, y2, a2), b2 = fma(a5, y2, a4);
+      sm.kv[s][p] = fma(b2, y8, fma(b1, y4, b0));
+    }
+    sm.kv[s][SP_W] = 0.0;
+  }
+#endif
 #pragma unroll
   for (int c = 0; c < 2; c++) { sm.rec[s][SP_C + 2 * c] = V[c] * cs; sm.rec[s][SP_C + 2 * c + 1] = V[c] * sn; }   // (Re, Im) per component
   return (int)L0;
@@ -137,6 +162,10 @@ SRB_HD void spread_close_window(WarpSmem<C>& sm, int lane, ThreadState<C>& st) {
 }
 
 struct SpreadStep { double y, y2, y4, y8, c[4]; };
+#if defined(SRB_SPREAD_V2)
+template <class C> SRB_HD void main_spread_v2(const Params&, WarpSmem<C>&, int, uint32_t, int, ThreadState<C>&);
+template <class C> SRB_HD void spread_close_window(WarpSmem<C>&, int, ThreadState<C>&);
+#endif
 
 template <class C>
 SRB_HD SpreadStep spread_read_step(const WarpSmem<C>& sm, int s) {
@@ -169,6 +198,10 @@ SRB_HD double spread_kernel_value(const ThreadState<C>& st, const SpreadStep& r)
 // together (independent dependency chains).
 template <class C>
 SRB_HD void main_spread(const Params& P, WarpSmem<C>& sm, int cnt, uint32_t fullMask, int lane, ThreadState<C>& st) {
+#if defined(SRB_SPREAD_V2)
+  main_spread_v2<C>(P, sm, cnt, fullMask, lane, st);
+  return;
+#endif
   uint32_t same = 0u;
 #if defined(__CUDA_ARCH__)
   {
@@ -215,6 +248,58 @@ SRB_HD void main_spread(const Params& P, WarpSmem<C>& sm, int cnt, uint32_t full
     }
   }
 }
+
+#if defined(SRB_SPREAD_V2)
+// SRB_SPREAD_V2 main phase (lane = window cell): the kernel values were computed by the prep phase with lane = step
+// (143 DFMAs per lane and sub-batch instead of 11 per lane and STEP), so what is left per step is one predicated
+// load of this cell's value, the broadcast strengths and 4 FMAs -- a dense, branch-free loop over the 16 steps of
+// a half sub-batch once a pre-check has established that they all fit the 32-cell window.
+// Validated on the CPU emulation only (tests/test_emulated_kernels.py::test_gridding_kernel_v2_logic); to be
+// measured and GPU-validated before it replaces the loop above.
+template <class C>
+SRB_HD void main_spread_v2(const Params& P, WarpSmem<C>& sm, int cnt, uint32_t fullMask, int lane, ThreadState<C>& st) {
+  for (int half = 0; half < 2; half++) {
+    const uint32_t mask = fullMask & (half ? 0xffff0000u : 0x0000ffffu);
+    if (!mask) continue;
+#if defined(__CUDA_ARCH__)
+    const int first = __ffs((int)mask) - 1, last = 31 - __clz((int)mask);
+#else
+    const int first = __builtin_ctz(mask), last = 31 - __builtin_clz(mask);
+#endif
+    const int Lf = (int)(sm.rng[first] & 0x3ffu) - 16, Ll = (int)(sm.rng[last] & 0x3ffu) - 16;
+    if (!st.have) { st.W0 = Lf; st.have = 1; }
+    if (((Ll - st.W0) & (SP_N - 1)) > 32 - SP_W) {          // the half would leave the window: write it out, re-anchor
+      spread_close_window<C>(sm, lane, st);
+      st.W0 = Lf; st.have = 1;
+    }
+    const bool fits = ((Ll - st.W0) & (SP_N - 1)) <= 32 - SP_W;   // tau is monotone, so every step of the half fits
+    const int base = 16 * half;
+    if (fits) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int s = base + i;
+        if (!((mask >> s) & 1u)) continue;
+        const int d = ((int)(sm.rng[s] & 0x3ffu) - 16 - st.W0) & (SP_N - 1);
+        const int p = lane - d;
+        const double k = (unsigned)p < (unsigned)SP_W ? sm.kv[s][p] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) st.sacc[c] = fma(k, sm.rec[s][SP_C + c], st.sacc[c]);
+      }
+    } else {                                                  // > 19 cells of drift within 16 steps: step by step
+      for (int i = 0; i < 16; i++) {
+        const int s = base + i;
+        if (!((mask >> s) & 1u)) continue;
+        const int L0 = (int)(sm.rng[s] & 0x3ffu) - 16;
+        if (((L0 - st.W0) & (SP_N - 1)) > 32 - SP_W) { spread_close_window<C>(sm, lane, st); st.W0 = L0; st.have = 1; }
+        const int p = lane - ((L0 - st.W0) & (SP_N - 1));
+        const double k = (unsigned)p < (unsigned)SP_W ? sm.kv[s][p] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) st.sacc[c] = fma(k, sm.rec[s][SP_C + c], st.sacc[c]);
+      }
+    }
+  }
+}
+#endif
 
 SRB_HD int sp_bitrev9(int v) {
   int r = 0;

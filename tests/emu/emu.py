@@ -18,18 +18,24 @@ _SRC = [os.path.join(_HERE, 'emu.cpp'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_spread.cuh')]
 
 
-def build():
-    if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in _SRC):
+def build(so=None, defines=()):
+    so = so or _SO
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in _SRC):
         return
     subprocess.check_call(['/usr/bin/g++', '-std=c++17', '-O2', '-mfma', '-ffp-contract=off', '-fopenmp',
-                           '-shared', '-fPIC', '-o', _SO, _SRC[0]])
+                           *[f'-D{d}' for d in defines], '-shared', '-fPIC', '-o', so, _SRC[0]])
+
+
+_SO_V2 = os.path.join(_HERE, 'libsrb_emu_spread_v2.so')      # srb_spread.cuh with -DSRB_SPREAD_V2 (not the shipped loop)
 
 
 def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSnaps=1,
-        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True):
+        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True, spread_v2=False):
     """Returns (radiation dict in host layout, counters)."""
     build()
-    lib = ctypes.CDLL(_SO)
+    if spread_v2:
+        build(_SO_V2, ('SRB_SPREAD_V2',))
+    lib = ctypes.CDLL(_SO_V2 if spread_v2 else _SO)
     A = dict(Args)
     A, dtype = host.init_args(A)
     A['sigma_particle'] = dtype(sigma_particle)

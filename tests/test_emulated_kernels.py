@@ -219,3 +219,30 @@ def test_gridding_tables():
     for i in (0, 77, 128, 255):
         ft = np.trapezoid(psi * np.cos(2 * np.pi * (i - 128) / 512 * uq), uq)
         assert abs(dec[i] * ft - 1) < 1e-8
+
+
+def test_gridding_kernel_v2_logic(oracle):
+    """-DSRB_SPREAD_V2 (srb_spread.cuh; NOT the shipped configuration): kernel values evaluated by the prep phase
+    with lane = step, dense branch-free accumulation loop with lane = cell.  Logic check on the emulation so that the
+    next round only has to measure it: equal to the shipped loop to rounding, and to the oracle."""
+    tr, dt = cases.c5_tracks_numpy(3, 500)
+    tr = [t[:7] + [s] for t, s in zip(tr, (0, 4, 9))]
+    for grid in ((256, 3, 2), (100, 2, 2)):
+        args = cases.c5_args(grid=grid)
+        for kw in (dict(), dict(comp='cartesian', nSnaps=3, it_range=(0, 480)),
+                   dict(comp='cartesian_complex', sigma_particle=1e-5)):
+            ref = oracle.calculate_spectrum(args, tr, dt, **kw)
+            v1, _ = emu.run(args, tr, dt, kind='spread', **kw)
+            v2, cnt = emu.run(args, tr, dt, kind='spread', spread_v2=True, nPC=2, **kw)
+            for key, r in ref['radiation'].items():
+                assert max(rel_errors(v2[key], r)) < 1e-10, (grid, kw, key)
+                assert max(rel_errors(v2[key], v1[key])) < 1e-13, (grid, kw, key)
+    # fast drift (large angles, coarse time step): windows are re-anchored inside a half sub-batch
+    args = cases.c5_args(grid=(256, 2, 2))
+    args['grid'][1] = (0.05, 0.12)
+    ref = oracle.calculate_spectrum(args, tr, dt)
+    v2, cnt = emu.run(args, tr, dt, kind='spread', spread_v2=True)
+    v1, _ = emu.run(args, tr, dt, kind='spread')
+    assert max(rel_errors(v2['total'], ref['radiation']['total'])) < 1e-9
+    assert max(rel_errors(v2['total'], v1['total'])) < 1e-12
+    assert cnt[0] == ref['passed']
