@@ -83,6 +83,26 @@ def run_many(requests, cxxflags=None, threads=None, backend='clshim'):
             return pickle.load(f)
 
 
+def run_script(path, backend='clshim', threads=None, seed=None):
+    """Execute one of the reference's own scripts (e.g. /root/reference/tests/test_undulator_analytic.py) UNMODIFIED
+    in a child process, on the stand-ins (`backend='clshim'`: the reference's kernels compiled for the host) or on
+    the product's PyOpenCL-signature binding with emulated kernels (`backend='compat_emu'`).  `seed` seeds
+    numpy's global RNG before the script starts (the scripts draw their energy spread unseeded).  Returns stdout."""
+    if not available():
+        raise RuntimeError(f'reference not found under {REFERENCE_ROOT}')
+    env = dict(os.environ)
+    env.pop('PYTHONPATH', None)
+    env['SYNCHRAD_REFERENCE_BACKEND'] = backend
+    if threads is not None:
+        env['OMP_NUM_THREADS'] = str(threads)
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--script', os.path.abspath(path),
+                            '' if seed is None else str(int(seed))], env=env, cwd=tmp, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('reference script failed:\n' + r.stdout[-2000:] + r.stderr[-4000:])
+    return r.stdout
+
+
 def _intern(v):
     """calc.py compares option strings with `is`; literals are interned, unpickled strings are not."""
     if isinstance(v, str):
@@ -96,7 +116,7 @@ def _intern(v):
     return v
 
 
-def _child(req_path, out_path):
+def _child_setup():
     import warnings
     warnings.filterwarnings('ignore', category=SyntaxWarning)
     bad = {os.path.abspath(p or os.getcwd()) for p in (_REPO, _HERE)}
@@ -124,6 +144,10 @@ def _child(req_path, out_path):
             if rc != 0:
                 raise RuntimeError('emulator has no such configuration')
         pyopencl._integrate_host = emu_integrate_host
+
+
+def _child(req_path, out_path):
+    _child_setup()
     import numpy as np
     with open(req_path, 'rb') as f:
         req = _intern(pickle.load(f))
@@ -167,4 +191,12 @@ def _child(req_path, out_path):
 
 
 if __name__ == '__main__':
-    _child(sys.argv[1], sys.argv[2])
+    if sys.argv[1] == '--script':
+        _child_setup()
+        import runpy
+        if sys.argv[3]:
+            import numpy
+            numpy.random.seed(int(sys.argv[3]))
+        runpy.run_path(sys.argv[2], run_name='__main__')
+    else:
+        _child(sys.argv[1], sys.argv[2])
