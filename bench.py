@@ -296,7 +296,7 @@ def run_product(a):
     elif int(info.kind) == 4:    # pair kernel kept on the scalar pipe
         issued = (4 + 2 * nc * tw) / tw
     mma = int(info.kind) == 3 and a.dtype == 'double' and (tw * nc) % 8 == 0
-    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair, DMMA' if mma else 'pair', 4: 'pair, DFMA', 5: 'gridding (NUFFT)'}[int(info.kind)]
+    kname = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair, DMMA' if mma else 'pair', 4: 'pair, DFMA'}[int(info.kind)]
     roofline = {
         'bound': 'fp64_pipe' if a.dtype == 'double' else 'fp32_pipe',
         'achieved': achieved / 1e12, 'peak': peak.value / 1e12, 'unit': 'Tslot/s (FMA-pipe lane issue slots)',
@@ -353,7 +353,7 @@ def main():
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     p.add_argument('--dtype', default='double', choices=['double', 'float'])
-    p.add_argument('--phasor', default='auto', choices=['auto', 'direct', 'recur', 'pair', 'pair_fma', 'spread'])
+    p.add_argument('--phasor', default='auto', choices=['auto', 'direct', 'recur', 'pair', 'pair_fma'])
     p.add_argument('--particles-per-gpu', type=int, default=12500)
     p.add_argument('--track-steps', type=int, default=10000)
     p.add_argument('--e2e-steps', type=int, default=2)

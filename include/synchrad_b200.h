@@ -66,9 +66,7 @@ extern "C" {
                                field); fp64: the accumulation over steps runs as a GEMM on the FP64 tensor cores
                                (DMMA.8x8x4) when tile width x components is a multiple of 8 */
 #define SRB_PHASOR_PAIR_FMA 4 /* the pair kernel with the accumulation kept on the scalar FP64 pipe (DFMA) */
-#define SRB_PHASOR_SPREAD 5 /* EXPERIMENTAL opt-in: all-pass steps as a type-1 non-uniform FFT (spreading onto a 2x
-                               oversampled 512-cell grid + one FFT per track; srb_spread.cuh).  Far field, fp64,
-                               total/cartesian comps, ascending uniform grids with <= 256 omega nodes; else an error */
+/* (5 was the experimental gridding kernel of round 1; removed, see profiles/r02_spread_v2_decision.txt) */
 
 /* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
  * Tables are float64 arrays with the content `_init_data` uploads (calc.py:486-512): omega is

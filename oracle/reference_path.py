@@ -40,6 +40,8 @@ CTYPES = {'double': 0, 'float': 1, 'longdouble': 2}
 
 from scipy.constants import alpha as alpha_fs, c as _c, hbar as _hbar   # utils.py:3-4
 
+_trapz = getattr(np, 'trapezoid', None) or np.trapz
+
 J_in_um = 2e6 * np.pi * _hbar * _c  # utils.py:16
 
 
@@ -290,11 +292,11 @@ def get_energy_spectrum(res, **kw):
     if A['mode'] == 'far':
         th = 0.5 * (A['theta'][1:] + A['theta'][:-1])
         v = 0.5 * (val[:, 1:, :] + val[:, :-1, :])
-        return A['dph'] * np.trapezoid(v * np.sin(th)[None, :, None], th, axis=1).sum(-1)
+        return A['dph'] * _trapz(v * np.sin(th)[None, :, None], th, axis=1).sum(-1)
     r = A['radius']
-    return A['dph'] * np.trapezoid(val * r[None, :, None], r, axis=1).sum(-1)
+    return A['dph'] * _trapz(val * r[None, :, None], r, axis=1).sum(-1)
 
 
 def get_energy(res, **kw):
     """utils.py:95-102"""
-    return np.trapezoid(get_energy_spectrum(res, **kw), res['Args']['omega'])
+    return _trapz(get_energy_spectrum(res, **kw), res['Args']['omega'])

@@ -6,7 +6,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 OUT = os.path.join(CSRC, 'libsynchrad_b200.so')
 SOURCES = ['srb_api.cu']
-DEPS = ['srb_api.cu', 'srb_core.cuh', 'srb_pair.cuh', 'srb_literal.cuh', os.path.join('..', '..', 'include', 'synchrad_b200.h')]
+# every source under csrc/ is compiled into the one library (srb_api.cu includes the rest)
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))) + [os.path.join('..', '..', 'include', 'synchrad_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC', '-diag-suppress', '177']
 

@@ -135,6 +135,12 @@ class SynchRad(Utilities):
         self._native = bool(self.Args.get('native', False)) and self.dtype is np.single \
             and host.float_mode(self.Args) == 'mixed'
         self._phasor = self.Args.get('phasor', 'auto')    # extension: 'auto' | 'direct' | 'recur' | 'pair' | 'pair_fma'
+        if self.Args.get('native', False) and self.rank == 0:
+            if not self._native:
+                print("NOTE: 'native' is honoured for dtype='float' (mixed mode) only (SURVEY Q9); ignored here")
+            elif self._phasor != 'direct' and host.omega_is_uniform(self.Args):
+                print("NOTE: 'native' selects the MUFU sincos of the per-node (phasor='direct') kernel; on a uniform "
+                      "omega grid the planner uses the pair/recurrence kernels, which evaluate no per-node sincos")
 
     def _set_snap_iterations(self, it_range, nSnaps):
         self.snap_iterations = host.snap_iterations(it_range, nSnaps)
@@ -263,7 +269,7 @@ class SynchRad(Utilities):
         self.last_run = {
             'passed_updates': int(c[0]), 'visited_updates': int(c[1]),
             'updates': upd * int(self.Args['numGridNodes']), 'batches': len(batches),
-            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair_fma', 5: 'spread'}[int(res.info.kind)], 'integrate_ms': ms,
+            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair_fma'}[int(res.info.kind)], 'integrate_ms': ms,
             'tile_width': int(res.info.tile_width), 'particle_chunks': int(res.info.n_particle_chunks),
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
             'h2d_bytes': h2d,

@@ -42,15 +42,11 @@ int fail(const std::string& m) { g_err = m; return -1; }
 #ifndef SRB_MINB_DIRECT
 #define SRB_MINB_DIRECT 2
 #endif
-#ifndef SRB_MINB_SPREAD
-#define SRB_MINB_SPREAD 2
-#endif
 constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 
 // resident blocks per SM the register budget is tuned for: accumulators must stay in registers
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
-  if (C::KIND == srb::KIND_SPREAD) return SRB_MINB_SPREAD;   // 21 KB of shared memory per warp (512-cell grid)
   if (C::KIND == srb::KIND_DIRECT || C::KIND == srb::KIND_LITERAL) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
   if (C::MMA) return C::NACC > 48 ? 2 : SRB_MINB_MMA;   // 16-node tiles: 64 fp64 accumulators per lane
   if (C::PAIR && sizeof(typename C::TM) == 8) return SRB_MINB > 3 ? 3 : SRB_MINB;   // measured: 168 regs beat 128
@@ -216,8 +212,6 @@ __global__ void k_pipe_peak(T* out, T a, T b, int iters) {
   if (s == (T)123.456) out[0] = s;
 }
 
-__device__ double g_spread_tab[srb::SP_TAB_SIZE];
-
 struct Launcher {
   void (*kernel)(const srb::Params);
   size_t smem;
@@ -228,7 +222,7 @@ template <class C> Launcher make_launcher() {
   return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK};
 }
 
-using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::KIND_PAIR_FMA; using srb::KIND_SPREAD; using srb::MODE_FAR; using srb::MODE_NEAR;
+using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::KIND_PAIR_FMA; using srb::MODE_FAR; using srb::MODE_NEAR;
 
 // kind, mode, dtype, native, tile width, far components -> kernel
 bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* L) {
@@ -255,9 +249,7 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   SRB_BOTH(KIND_PAIR, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 4, 3) SRB_BOTH(KIND_PAIR, MODE_FAR, false, 2, 3)   // spheric kernels
   // the same kernel without tensor cores, where KIND_PAIR uses them (fp64, TW*NC % 8 == 0); phasor = SRB_PHASOR_PAIR_FMA
   SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 8, 2, double) SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 4, 2, double)
-  SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 8, 3, double)
-  // gridding (type-1 NUFFT) kernel: far field, fp64, transverse basis, <= 256 omega nodes (srb_spread.cuh)
-  SRB_CASE(KIND_SPREAD, MODE_FAR, 0, false, 8, 2, double)
+  SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 8, 3, double) SRB_CASE(KIND_PAIR_FMA, MODE_FAR, 0, false, 16, 2, double)
   // literal fp32 (dtype 2)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 8, 3, float) SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 4, 3, float)
   SRB_CASE(KIND_LITERAL, MODE_FAR, 2, false, 2, 3, float)
@@ -317,11 +309,6 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (g->phasor == SRB_PHASOR_AUTO && g->mode == SRB_MODE_NEAR && g->dtype == SRB_DTYPE_F64 &&
       std::fabs(g->omega_last_host * g->L_screen) > 262144.0)
     p->kind = KIND_DIRECT;
-  if (g->phasor == SRB_PHASOR_SPREAD) {
-    if (!pairOk || spheric || g->dtype != SRB_DTYPE_F64 || g->nOmega > 256)
-      return fail("the gridding kernel needs the far field, fp64, total/cartesian comps and an ascending uniform omega grid of <= 256 nodes");
-    p->kind = KIND_SPREAD;
-  }
   if (g->dtype == SRB_DTYPE_F32_LITERAL) p->kind = KIND_LITERAL;
   p->native = (p->kind == KIND_DIRECT && g->dtype == SRB_DTYPE_F32 && g->native != 0);   // Q9
   const int tiles = p->kind == KIND_RECUR ? 16 : 32;
@@ -329,7 +316,6 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
   else if (p->kind == KIND_PAIR) { twMax = !spheric ? 16 : 8; twMin = 2; }
-  else if (p->kind == KIND_SPREAD) { twMax = twMin = 8; }   // one chunk of up to 256 nodes
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }
@@ -337,7 +323,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
     const int tw = std::atoi(f);
     if (tw >= twMin && tw <= twMax && (tw & (tw - 1)) == 0) p->tw = tw;
   }
-  p->nc = ((p->kind == KIND_PAIR || p->kind == KIND_RECUR || p->kind == KIND_SPREAD) && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
+  p->nc = ((p->kind == KIND_PAIR || p->kind == KIND_RECUR) && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
   // SRB_PHASOR_PAIR_FMA: scalar-pipe accumulation; only differs where the pair kernel would use DMMA
   if (g->phasor == SRB_PHASOR_PAIR_FMA && p->kind == KIND_PAIR && g->dtype == SRB_DTYPE_F64 && (p->tw * p->nc) % 8 == 0)
     p->kind = KIND_PAIR_FMA;
@@ -458,21 +444,6 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   P.pre = preBuf; P.preStride = t->totalSteps_host;
   P.slabs = (double*)scratch + p.preDoubles; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
   P.counters = (unsigned long long*)counters;
-  if (p.kind == KIND_SPREAD) {
-    // kernel-polynomial / deconvolution / twiddle tables: constant content, built once on the host, refreshed on
-    // this device on the caller's stream (7.7 KB)
-    static double hostTab[srb::SP_TAB_SIZE];
-    static std::once_flag once;
-    std::call_once(once, [] { srb::spread_build_tables(hostTab); });
-    SRB_CUDA(cudaMemcpyToSymbolAsync(g_spread_tab, hostTab, sizeof hostTab, 0, cudaMemcpyHostToDevice, stream));
-#if defined(SRB_SPREAD_V2)
-    SRB_CUDA(cudaMemcpyToSymbolAsync(srb::c_spread_coef, hostTab + srb::SP_TAB_COEF, sizeof(double) * (srb::SP_DEG + 1) * 16, 0, cudaMemcpyHostToDevice, stream));
-#endif
-    void* addr = nullptr;
-    SRB_CUDA(cudaGetSymbolAddress(&addr, g_spread_tab));
-    P.spreadTab = (const double*)addr;
-  }
-
   uint32_t launched = 0;
   if (preBuf) {
     const uint64_t total = t->totalSteps_host;

@@ -57,7 +57,9 @@ namespace srb {
 
 enum { MODE_FAR = 0, MODE_NEAR = 1 };
 enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
-enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3, KIND_PAIR_FMA = 4, KIND_SPREAD = 5 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh, SPREAD: srb_spread.cuh
+enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3, KIND_PAIR_FMA = 4 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh
+// (kind 5 was the experimental gridding / type-1 NUFFT kernel of round 1: correct but 0.75-0.81x the pair kernel after two
+//  iterations, profiles/r02_spread_v2_decision.txt; removed from the library, kept on the git branch `spread-kernel`)
 // KIND_PAIR_FMA: the pair kernel with its accumulation on the scalar FP64 pipe (DFMA) where KIND_PAIR uses DMMA
 constexpr int SUB = 32;  // steps per sub-batch (= lanes of the prep phase)
 
@@ -219,8 +221,6 @@ struct Params {
   // near: beta0,beta1,beta2.  nullptr -> the prep phase computes them itself.
   const double* pre;
   uint64_t preStride;
-  // KIND_SPREAD: kernel-polynomial / deconvolution / twiddle tables (srb_spread.cuh: spread_build_tables)
-  const double* spreadTab;
 };
 
 // NC: amplitude components carried per node in far-field mode.
@@ -235,7 +235,6 @@ struct Cfg {
   using TM = TM_;   // arithmetic type of the main phase
   static constexpr int MODE = MODE_, KIND = KIND_, TW = TW_, NC = NC_;
   static constexpr bool PAIR = KIND_ == KIND_PAIR || KIND_ == KIND_PAIR_FMA;
-  static constexpr bool SPREAD = KIND_ == KIND_SPREAD;   // gridding (type-1 NUFFT) main phase, direct accumulator layout
   static constexpr bool NATIVE = NATIVE_;
   static constexpr int TILES = (KIND_ == KIND_RECUR) ? 16 : 32;   // omega tiles per chunk
   static constexpr int CHUNK = TILES * TW_;
@@ -243,7 +242,7 @@ struct Cfg {
   // accumulators per node: split layout (recurrence) holds one part (cos or sin) of NV sums,
   // the direct layout holds Re and Im of the 3 (far: NC) amplitude components
   static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV
-      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || PAIR || SPREAD)) ? 2 * NC_ : 6);
+      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || PAIR)) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
   //          (pair) V[NC], tau (flag 3 only), pad to QOFF, then A_c*(cos,sin) of the TW/2 pair offsets for
@@ -261,39 +260,20 @@ struct Cfg {
   static constexpr int NREC_FLUSH = MMA ? (((32 * NACC - 16 - NSEED * 33 + 31) / 32 + 3) & ~3) : 0;
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
       : PAIR ? (NREC_PAIR > NREC_FLUSH ? NREC_PAIR : NREC_FLUSH)
-      : SPREAD ? 12                              // V[NC], tau, -, y, y^2, y^4, y^8, (Re, Im) c[NC] (srb_spread.cuh)
       : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
 };
 
-constexpr int SP_N = 512;      // oversampled grid cells (2 x 256 nodes)
-constexpr int SP_W = 13;       // kernel width in cells
-constexpr int SP_DEG = 11;     // degree of the per-cell polynomial pieces
-template <bool ON> struct SpreadSmem {};
-template <> struct alignas(16) SpreadSmem<true> {   // 16-byte alignment: 128-bit shared-memory loads of the step records
-  double grid[SP_N][4];                 // per cell: Re, Im of the two transverse components
-  double coef[SP_DEG + 1][16];          // [power][piece]
-#if defined(SRB_SPREAD_V2)
-  double kv[SUB][SP_W + 1];             // kernel values of every step's 13 cells, written by the prep phase (lane = step)
-#endif
-};
-template <bool ON> struct SpreadState {};
-template <> struct SpreadState<true> {
-  double cf[SP_DEG + 1];                // this lane's polynomial piece (cell = window anchor + lane)
-  double sacc[4];                       // window accumulators of this lane's cell
-  int W0, curM, have, dirty;            // warp-uniform: window anchor, piece shift, window open, grid holds data
-};
-
 template <class C>
-struct WarpSmem : SpreadSmem<C::KIND == KIND_SPREAD> {
+struct WarpSmem {
   typename C::TM rec[SUB][C::NREC];       // per-step record (see Cfg::NREC)
   uint32_t rng[SUB];                      // lo | hi<<10 | flag<<30 (chunk-relative pass range)
   typename C::TM seeds[C::NSEED][SUB + 1];  // [part*16+tile][step]: cos|sin of the tile's first node
 };
 
 template <class C>
-struct ThreadState : SpreadState<C::KIND == KIND_SPREAD> {
+struct ThreadState {
   typename C::TM acc[C::NACC];
-  typename C::TM wl[(C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL || C::KIND == KIND_SPREAD) ? C::TW : 1];   // this lane's omega nodes
+  typename C::TM wl[(C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) ? C::TW : 1];   // this lane's omega nodes
   typename C::TM pprev[C::KIND == KIND_LITERAL ? C::TW : 1];   // literal kind: per-node phasePrev
   typename C::TM ff[C::KIND == KIND_LITERAL ? C::TW : 1];      // literal kind: per-node FormFactor
   unsigned long long nPass, nAll;
@@ -348,14 +328,6 @@ template <class C> SRB_HD void pair_mma_load_frag(const WarpSmem<C>&, int, Threa
 template <class C> SRB_HD void pair_mma_load_tile(const WarpSmem<C>&, int, ThreadState<C>&);
 template <class C> SRB_HD void pair_mma_store_tile(WarpSmem<C>&, int, const ThreadState<C>&);
 template <class C> SRB_HD void pair_node_amp(const ThreadState<C>&, int, double*, double*);
-// gridding kind (srb_spread.cuh)
-template <class C> SRB_HD int spread_stage(const Params&, const Geom&, double, const double*, WarpSmem<C>&, int);
-template <class C> SRB_HD void spread_init(const Params&, WarpSmem<C>&, int, ThreadState<C>&);
-template <class C> SRB_HD void main_spread(const Params&, WarpSmem<C>&, int, uint32_t, int, ThreadState<C>&);
-template <class C> SRB_HD void spread_close_window(WarpSmem<C>&, int, ThreadState<C>&);
-template <class C> SRB_HD void spread_fft_stage(WarpSmem<C>&, const Params&, int, int);
-template <class C> SRB_HD void spread_extract(const Params&, const Geom&, WarpSmem<C>&, int, ThreadState<C>&);
-template <class C> SRB_HD void spread_clear(WarpSmem<C>&, int, ThreadState<C>&);
 // literal fp32 kind (srb_literal.cuh), used by warp_task below
 template <class C> SRB_HD void lit_prep_phase(const Params&, const Geom&, const TrackView&, uint32_t, int, int, WarpSmem<C>&);
 template <class C> SRB_HD void lit_main_phase(const Params&, const Geom&, const WarpSmem<C>&, int, int, ThreadState<C>&);
@@ -523,20 +495,10 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, V);
   else prep_near<C>(P, g, tv, it, r0, r1, r2, rL, V, V + 3);
   double last[3] = {tau, 0.0, 0.0};
-  int spreadL0 = 0;   // gridding kind: first grid cell of an all-pass step (in [-6, 506])
   if constexpr (C::PAIR) {
     const double wl = (double)((const typename C::TI*)P.omega)[g.cHi - 1];
     if (sizeof(TM) == 8 && fabs(wl * tau) > 262144.0) flag = 3u;
     else make_seeds_pair<C>(P, g, tau, V, sm, lane);
-  }
-  if constexpr (C::KIND == KIND_SPREAD) {
-    // gridding tracks the reference's rounded phase to ~1e-16*|phase| like the pair kernel: same 2^18 limit,
-    // beyond it the step is evaluated node by node (flag 3, full range)
-    const double wl = (double)((const typename C::TI*)P.omega)[g.cHi - 1];
-    if (flag == 1u) {
-      if (fabs(wl * tau) > 262144.0) flag = 3u;
-      else spreadL0 = spread_stage<C>(P, g, tau, V, sm, lane);
-    }
   }
   if (C::KIND == KIND_RECUR) {
     // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
@@ -547,7 +509,6 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
     if (big) flag = 3u; else make_seeds<C>(P, g, tau, sm, lane, last);
   }
   sm.rng[lane] = lo | (hi << 10) | (flag << 30);
-  if (C::KIND == KIND_SPREAD && flag == 1u) sm.rng[lane] = (uint32_t)(spreadL0 + 16) | (1u << 30);   // all-pass: the range is implied
   st.nPass += hi - lo;
 #pragma unroll
   for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
@@ -757,7 +718,7 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
     double re[3], im[3];
     if constexpr (C::PAIR) {
       pair_node_amp<C>(me, k, re, im);
-    } else if constexpr (C::KIND == KIND_DIRECT || C::KIND == KIND_SPREAD) {
+    } else if constexpr (C::KIND == KIND_DIRECT) {
 #pragma unroll
       for (int c = 0; c < NCF; c++) { re[c] = (double)me.acc[k * NPN + c]; im[c] = (double)me.acc[k * NPN + NCF + c]; }
     } else {
@@ -871,8 +832,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
   }
   SRB_LANES_BEGIN
     SRB_ST.nPass = 0; SRB_ST.nAll = 0;
-    if constexpr (C::KIND == KIND_SPREAD) spread_init<C>(P, sm, lane, SRB_ST);
-    if (C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL || C::KIND == KIND_SPREAD) {
+    if (C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) {
 #pragma unroll
       for (int k = 0; k < C::TW; k++) {
         const uint32_t j = g.cLo + (uint32_t)(lane + 32 * k);
@@ -963,37 +923,9 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
 #endif
           }
           else if constexpr (C::PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
-          else if constexpr (C::KIND == KIND_SPREAD) {
-            // all-pass steps are gridded; partial / huge-phase steps go node by node into the same accumulators
-#if !defined(SRB_SPREAD_NO_MAIN)     // (tuning aid: time the prep phase alone)
-            if (fullMask) main_spread<C>(P, sm, cnt, fullMask, lane, SRB_ST);
-#endif
-            if (anyMask & ~fullMask) main_direct<C>(P, g, sm, cnt, 0u, anyMask & ~fullMask, lane, SRB_ST);
-          }
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
         }
-        }
-      }
-      if constexpr (C::KIND == KIND_SPREAD) {
-        // gridded contributions since the last flush: window -> grid, FFT, deconvolve into the node accumulators
-        bool any = false;
-        SRB_LANES_BEGIN
-          spread_close_window<C>(sm, lane, SRB_ST);
-          any = any || SRB_ST.dirty;
-        SRB_LANES_END
-        if (any) {
-          for (int stage = 0; stage < 9; stage++) {
-            SRB_LANES_BEGIN
-              spread_fft_stage<C>(sm, P, stage, lane);
-            SRB_LANES_END
-          }
-          SRB_LANES_BEGIN
-            spread_extract<C>(P, g, sm, lane, SRB_ST);
-          SRB_LANES_END
-          SRB_LANES_BEGIN
-            spread_clear<C>(sm, lane, SRB_ST);
-          SRB_LANES_END
         }
       }
       if constexpr (C::MMA) {

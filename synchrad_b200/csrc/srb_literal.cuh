@@ -15,7 +15,6 @@
 #pragma once
 #include "srb_core.cuh"
 #include "srb_pair.cuh"
-#include "srb_spread.cuh"
 
 namespace srb {
 

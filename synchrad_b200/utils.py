@@ -18,6 +18,9 @@ omega_1m = 2 * np.pi * c
 energy_1m_eV = omega_1m * hbar / e
 
 
+_trapz = getattr(np, 'trapezoid', None) or np.trapz      # NumPy >= 2.0 / 1.x (the reference calls np.trapz)
+
+
 class Utilities:
     """Mixin base of SynchRad (reference: `class SynchRad(Utilities)`, calc.py:21)."""
 
@@ -89,16 +92,16 @@ class Utilities:
             th = self.Args['theta']
             th_mid = 0.5 * (th[1:] + th[:-1])
             v_mid = 0.5 * (val[:, 1:, :] + val[:, :-1, :])
-            inner = np.trapezoid(v_mid * np.sin(th_mid)[None, :, None], th_mid, axis=1)
+            inner = _trapz(v_mid * np.sin(th_mid)[None, :, None], th_mid, axis=1)
         else:
             r = self.Args['radius']
-            inner = np.trapezoid(val * r[None, :, None], r, axis=1)
+            inner = _trapz(val * r[None, :, None], r, axis=1)
         return self.Args['dph'] * inner.sum(-1)
 
     def get_energy(self, spect_filter=None, phot_num=False, lambda0_um=None, on_device=False, **kw):
         val = self.get_energy_spectrum(spect_filter=spect_filter, phot_num=phot_num,
                                        lambda0_um=lambda0_um, on_device=on_device, **kw)
-        return np.trapezoid(val, self.Args['omega'])
+        return _trapz(val, self.Args['omega'])
 
     def get_spot(self, k0=None, spect_filter=None, phot_num=False, lambda0_um=None, **kw):
         """Angular map (theta|R, phi): the spectrum integrated over omega, or its slice at the node closest to
@@ -109,7 +112,7 @@ class Utilities:
         omega = self.Args['omega']
         if k0 is None:
             if val.shape[0] > 1:
-                return np.trapezoid(val, omega, axis=0)
+                return _trapz(val, omega, axis=0)
             return val[0] * self.Args['dw']
         below = int((omega < k0).sum())
         if np.abs(omega[below + 1] - k0) < np.abs(omega[below] - k0):

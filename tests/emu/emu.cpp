@@ -35,12 +35,6 @@ extern "C" void srb_emu_sincos(const double* x, double* s, double* c, long n) {
   for (long i = 0; i < n; i++) sincos_big(x[i], s + i, c + i);
 }
 
-// exposes the gridding tables for a direct check against the kernel's definition
-extern "C" int srb_emu_spread_tables(double* out) {
-  spread_build_tables(out);
-  return SP_TAB_SIZE;
-}
-
 extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int nOut,
                                  int kind, int tw, uint32_t nPC, unsigned long long* counters, int prepass) {
   Params P;
@@ -95,7 +89,6 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   bool ok = false;
   const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
   const int nc = (kind == KIND_RECUR && g->mode == SRB_MODE_FAR && !spheric) ? 2 : 3;
-  if (kind == KIND_SPREAD) tw = 8;
 #define EMU_CASE1(K, M, TWV, NCV)                                                               \
   if (kind == K && g->mode == M && tw == TWV && nc == NCV) {                                    \
     if (f32) run_all<Cfg<double, float, M, K, TWV, false, NCV>>(P, counters);                   \
@@ -123,14 +116,6 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
 #define EMU_LIT(M, TWV) if (kind == KIND_LITERAL && g->mode == M && tw == TWV) { run_all<Cfg<double, float, M, KIND_LITERAL, TWV, false, 3>>(P, counters); ok = true; }
   EMU_LIT(MODE_FAR, 8) EMU_LIT(MODE_FAR, 4) EMU_LIT(MODE_FAR, 2) EMU_LIT(MODE_NEAR, 8) EMU_LIT(MODE_NEAR, 4) EMU_LIT(MODE_NEAR, 2)
 #undef EMU_LIT
-  if (kind == KIND_SPREAD && g->mode == MODE_FAR && !f32 && !spheric && g->nOmega <= 256 && tw == 8) {
-    static double tab[SP_TAB_SIZE];
-    static bool built = false;
-    if (!built) { spread_build_tables(tab); built = true; }
-    P.spreadTab = tab;
-    run_all<Cfg<double, double, MODE_FAR, KIND_SPREAD, 8, false, 2>>(P, counters);
-    ok = true;
-  }
   if (!ok) return -1;
   for (uint32_t s = 0; s + 1 < nPC; s++)
     for (int c = 0; c < nOut; c++)
@@ -138,8 +123,4 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   return 0;
 }
 
-// layout facts the device code relies on (128-bit loads of the gridding kind's step records)
-static_assert(sizeof(WarpSmem<Cfg<double, double, MODE_FAR, KIND_SPREAD, 8, false, 2>>) % 16 == 0, "warp slices must stay 16-byte aligned");
-static_assert(alignof(WarpSmem<Cfg<double, double, MODE_FAR, KIND_SPREAD, 8, false, 2>>) == 16, "alignment of the gridding shared memory");
-static_assert(sizeof(SpreadSmem<true>) % 16 == 0, "step records (first member after the gridding base) 16-byte aligned");
 static_assert(sizeof(WarpSmem<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 2>>) == 32 * 20 * 8 + 128 + 24 * 33 * 8, "other kinds keep their footprint");

@@ -14,8 +14,7 @@ _SO = os.path.join(_HERE, 'libsrb_emu.so')
 _SRC = [os.path.join(_HERE, 'emu.cpp'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_pair.cuh'),
-        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh'),
-        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_spread.cuh')]
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh')]
 
 
 def build(so=None, defines=()):
@@ -26,16 +25,11 @@ def build(so=None, defines=()):
                            *[f'-D{d}' for d in defines], '-shared', '-fPIC', '-o', so, _SRC[0]])
 
 
-_SO_V2 = os.path.join(_HERE, 'libsrb_emu_spread_v2.so')      # srb_spread.cuh with -DSRB_SPREAD_V2 (not the shipped loop)
-
-
 def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSnaps=1,
-        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True, spread_v2=False):
+        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True):
     """Returns (radiation dict in host layout, counters)."""
     build()
-    if spread_v2:
-        build(_SO_V2, ('SRB_SPREAD_V2',))
-    lib = ctypes.CDLL(_SO_V2 if spread_v2 else _SO)
+    lib = ctypes.CDLL(_SO)
     A = dict(Args)
     A, dtype = host.init_args(A)
     A['sigma_particle'] = dtype(sigma_particle)
@@ -74,9 +68,7 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     keys = host.COMP_KEYS[comp]
     spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
     sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
-    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4, 'spread': 5}[kind]
-    if kind_i == 5:
-        tw = 8
+    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4}[kind]
     if literal:
         kind_i, tw = 0, None   # the C side switches to the literal kind; tile widths of the direct layout
     if tw is None:

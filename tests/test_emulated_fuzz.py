@@ -19,8 +19,6 @@ def test_random_problems_match_oracle(oracle, seed):
         kinds = ['direct'] if A.get('Features') or A['grid'][-1][0] < 2 else ['direct', 'recur']
         if 'recur' in kinds and A.get('mode', 'far') == 'far':
             kinds.append('pair')
-            if A['grid'][-1][0] <= 256 and not kw['comp'].startswith('spheric'):
-                kinds.append('spread')      # gridding kernel: same eligibility rule as make_plan (srb_api.cu)
         for kind in kinds:
             for nPC in (1, 3):
                 with contextlib.redirect_stdout(io.StringIO()):

@@ -164,85 +164,3 @@ def test_literal_fp32_mode_matches_the_fp32_oracle(oracle, near):
         assert cnt[0] == lit['passed'], (comp, cnt, lit['passed'])
         for k in rad:
             assert max(rel_errors(rad[k], lit['radiation'][k])) < 1e-6, (comp, k)
-
-
-@pytest.mark.parametrize('grid', [(256, 3, 2), (200, 2, 3), (33, 2, 2)])
-def test_gridding_kernel_logic(oracle, grid):
-    """KIND_SPREAD (srb_spread.cuh, phasor='spread'): all-pass steps as a type-1 non-uniform FFT -- window
-    spreading with the polynomial ES kernel, in-warp 512-point FFT, deconvolution -- plus node-by-node evaluation
-    of the partially passing steps; every comp it supports, snapshots (one FFT per interval), particle chunks."""
-    tr, dt = cases.c5_tracks_numpy(3, 500)
-    tr = [t[:7] + [s] for t, s in zip(tr, (0, 4, 9))]
-    args = cases.c5_args(grid=grid)
-    for kw in (dict(), dict(comp='cartesian', nSnaps=3, it_range=(0, 480)),
-               dict(comp='cartesian_complex', sigma_particle=1e-5)):
-        ref = oracle.calculate_spectrum(args, tr, dt, **kw)
-        for nPC in (1, 2):
-            rad, cnt = emu.run(args, tr, dt, kind='spread', nPC=nPC, **kw)
-            for key, r in ref['radiation'].items():
-                assert max(rel_errors(rad[key], r)) < 1e-10, (grid, kw, key, rel_errors(rad[key], r))
-            if 'it_range' not in kw:      # (steps after a track's last reachable flush are skipped by every kernel)
-                assert cnt[0] == ref['passed']
-    # guard-dominated input: most steps take the node-by-node path, the rest is gridded
-    trw, dtw, infow = cases.wiggler_tracks(4, 256)
-    argw = cases.wiggler_args(infow, grid=(grid[0], 3, 2))
-    ref = oracle.calculate_spectrum(argw, trw, dtw, comp='cartesian')
-    rad, cnt = emu.run(argw, trw, dtw, kind='spread', comp='cartesian')
-    for key, r in ref['radiation'].items():
-        assert max(rel_errors(rad[key], r)) < 1e-9, (key, rel_errors(rad[key], r))
-    assert cnt[0] == ref['passed']
-
-
-def test_gridding_tables():
-    """The kernel-polynomial pieces reproduce the ES kernel to 1e-9 of its peak (degree 11, width 13) and vanish
-    outside the support; the deconvolution factors are 1 / FT of the kernel."""
-    import ctypes
-    emu.build()
-    lib = ctypes.CDLL(emu._SO)
-    tab = (ctypes.c_double * 2048)()
-    n = lib.srb_emu_spread_tables(tab)
-    t = np.frombuffer(tab, dtype=np.double)[:n]
-    W, D, beta = 13, 11, 2.30 * 13
-    coef = t[:(D + 1) * 16].reshape(D + 1, 16)
-    assert not coef[:, W:].any()
-    tt = np.linspace(0, 1, 101)
-    for p in range(W):
-        u = p + tt - W / 2
-        z = 2 * u / W
-        exact = np.where(np.abs(z) < 1, np.exp(beta * (np.sqrt(np.clip(1 - z * z, 0, None)) - 1)), 0.0)
-        approx = np.polyval(coef[::-1, p], 2 * tt - 1)
-        assert np.abs(approx - exact).max() < 2e-9
-    dec = t[(D + 1) * 16:(D + 1) * 16 + 256]
-    uq = np.linspace(-W / 2, W / 2, 20001)
-    zq = 2 * uq / W
-    psi = np.where(np.abs(zq) < 1, np.exp(beta * (np.sqrt(np.clip(1 - zq * zq, 0, None)) - 1)), 0.0)
-    for i in (0, 77, 128, 255):
-        ft = np.trapezoid(psi * np.cos(2 * np.pi * (i - 128) / 512 * uq), uq)
-        assert abs(dec[i] * ft - 1) < 1e-8
-
-
-def test_gridding_kernel_v2_logic(oracle):
-    """-DSRB_SPREAD_V2 (srb_spread.cuh; NOT the shipped configuration): kernel values evaluated by the prep phase
-    with lane = step, dense branch-free accumulation loop with lane = cell.  Logic check on the emulation so that the
-    next round only has to measure it: equal to the shipped loop to rounding, and to the oracle."""
-    tr, dt = cases.c5_tracks_numpy(3, 500)
-    tr = [t[:7] + [s] for t, s in zip(tr, (0, 4, 9))]
-    for grid in ((256, 3, 2), (100, 2, 2)):
-        args = cases.c5_args(grid=grid)
-        for kw in (dict(), dict(comp='cartesian', nSnaps=3, it_range=(0, 480)),
-                   dict(comp='cartesian_complex', sigma_particle=1e-5)):
-            ref = oracle.calculate_spectrum(args, tr, dt, **kw)
-            v1, _ = emu.run(args, tr, dt, kind='spread', **kw)
-            v2, cnt = emu.run(args, tr, dt, kind='spread', spread_v2=True, nPC=2, **kw)
-            for key, r in ref['radiation'].items():
-                assert max(rel_errors(v2[key], r)) < 1e-10, (grid, kw, key)
-                assert max(rel_errors(v2[key], v1[key])) < 1e-13, (grid, kw, key)
-    # fast drift (large angles, coarse time step): windows are re-anchored inside a half sub-batch
-    args = cases.c5_args(grid=(256, 2, 2))
-    args['grid'][1] = (0.05, 0.12)
-    ref = oracle.calculate_spectrum(args, tr, dt)
-    v2, cnt = emu.run(args, tr, dt, kind='spread', spread_v2=True)
-    v1, _ = emu.run(args, tr, dt, kind='spread')
-    assert max(rel_errors(v2['total'], ref['radiation']['total'])) < 1e-9
-    assert max(rel_errors(v2['total'], v1['total'])) < 1e-12
-    assert cnt[0] == ref['passed']

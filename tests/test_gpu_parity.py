@@ -190,31 +190,6 @@ def test_on_device_energy_spectrum_matches_host_integrals(cuda_lib):
         assert torch.equal(a, b)
 
 
-def test_gridding_kernel_opt_in(cuda_lib, oracle):
-    """phasor='spread' (KIND_SPREAD, srb_spread.cuh; experimental opt-in): all-pass steps through a type-1
-    non-uniform FFT, the rest node by node -- same 1e-9 bar, identical guard counts; unsupported configurations
-    are refused, never silently rerouted."""
-    tr, dt = cases.c5_tracks_numpy(6, 700)
-    for grid in ((256, 4, 3), (200, 3, 2)):
-        args = cases.c5_args(grid=grid)
-        for kw in (dict(), dict(comp='cartesian', nSnaps=3), dict(comp='cartesian_complex', sigma_particle=1e-5)):
-            calc = run_gpu(args, tr, dt, phasor='spread', **kw)
-            ref = oracle.calculate_spectrum(args, tr, dt, **kw)
-            assert calc.last_run['kernel'] == 'spread'
-            assert_close(calc, ref['radiation'], what=f'spread {grid} {kw}')
-            assert calc.last_run['passed_updates'] == ref['passed']
-    trw, dtw, infow = cases.wiggler_tracks(6, 256)                      # guard-dominated: mostly the node-by-node path
-    argw = cases.wiggler_args(infow, grid=(256, 4, 3))
-    calc = run_gpu(argw, trw, dtw, phasor='spread', comp='cartesian')
-    ref = oracle.calculate_spectrum(argw, trw, dtw, comp='cartesian')
-    assert_close(calc, ref['radiation'])
-    assert calc.last_run['passed_updates'] == ref['passed']
-    for bad, kw in ((cases.c5_args(grid=(300, 2, 2)), {}), (cases.c5_args(grid=(64, 2, 2), dtype='float'), {}),
-                    (cases.c5_args(grid=(64, 2, 2)), dict(comp='spheric'))):
-        with pytest.raises(RuntimeError):
-            run_gpu(bad, tr, dt, phasor='spread', **kw)
-
-
 # ---------------------------------------------------------------------------- golden fixtures
 def test_golden_small_cases(cuda_lib):
     import golden.make_golden as mg
@@ -466,8 +441,6 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
                 phasors = ('auto',)
             else:
                 phasors = ('auto', 'recur', 'direct') if far_plain else ('auto', 'direct')
-                if far_plain and A['grid'][-1][0] <= 256 and not kw['comp'].startswith('spheric'):
-                    phasors += ('spread',)           # the opt-in gridding kernel, wherever make_plan accepts it
             for phasor in phasors:
                 calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
                 e = fuzzcases.vector_errors(calc.Data['radiation'], ref['radiation'])

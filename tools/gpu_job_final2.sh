@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
 timeout 200 python -m pytest tests -m gpu -q -x > gpurun_out/final2_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/final2_pytest_gpu.txt
-python tools/quick_perf.py 592 10000 double spread 2 2>/dev/null | tee -a gpurun_out/spread_perf.txt
