@@ -36,6 +36,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define SRB_HD __host__ __device__ __forceinline__
@@ -178,17 +179,44 @@ SRB_HD void sincos_t(float x, float* s, float* c) {
   *s = sinf(x); *c = cosf(x);
 #endif
 }
-// fp32 'native' path (calc.py:612-615 -> native_sin/native_cos): explicit 2-term Cody-Waite
-// reduction to [-pi,pi] in fp32, then the MUFU approximations.
-SRB_HD void sincos_native(float x, float* s, float* c) {
+// (fp32 'native' path, calc.py:612-615 -> native_sin/native_cos: see sincos_mixed<true>)
+// fp32 main phase of the DIRECT kind (mixed precision): the phase omega*tau is formed in fp64 (a phase rounded to
+// fp32 is already 2^-24*|phase| = 1e-4 rad off at 2000 rad) and reduced there -- 1 DMUL + 4 DFMA on the FP64 pipe,
+// which this kernel leaves idle -- to r in [-pi/4, pi/4] + quadrant; sin/cos of r are fp32 minimax polynomials
+// (Cephes sinf/cosf kernels, ~1e-7).  NATIVE: reduction to [-pi, pi], then the MUFU approximations.
+template <bool NATIVE>
+SRB_HD void sincos_mixed(double w, double tau, float* sn, float* cs) {
+  const double ph = smul(w, tau);
 #if defined(__CUDA_ARCH__)
-  const float q = rintf(x * 0.15915494309189535f);
-  float r = fmaf(-q, 6.2831854820251465f, x);     // 2*pi rounded to fp32
-  r = fmaf(-q, -1.7484555e-7f, r);                // 2*pi - fp32(2*pi)
-  __sincosf(r, s, c);
-#else
-  *s = sinf(x); *c = cosf(x);
+  if (NATIVE) {
+    const double t = fma(ph, 0.15915494309189535, 6755399441055744.0);
+    const double qd = ssub(t, 6755399441055744.0);
+    double r = fma(qd, -6.283185307179586, ph);
+    r = fma(qd, -2.4492935982947064e-16, r);
+    __sincosf((float)r, sn, cs);
+    return;
+  }
 #endif
+  const double t = fma(ph, 0.6366197723675814, 6755399441055744.0);
+  const double qd = ssub(t, 6755399441055744.0);
+#if defined(__CUDA_ARCH__)
+  const uint32_t q = (uint32_t)__double2loint(t);
+#else
+  uint64_t tb; memcpy(&tb, &t, 8);
+  const uint32_t q = (uint32_t)tb;
+#endif
+  double rd = fma(qd, -1.5707963267948966, ph);
+  rd = fma(qd, -6.123233995736766e-17, rd);
+  const float r = (float)rd, z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(z, ps, -1.6666654611e-1f);
+  const float s = fmaf(r * z, ps, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(z, pc, 4.166664568298827e-2f);
+  const float c = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+  const float a = (q & 1u) ? c : s, b = (q & 1u) ? s : c;
+  *sn = flipsign(a, (q & 2u) << 30);
+  *cs = flipsign(b, ((q + 1u) & 2u) << 30);
 }
 
 // ---- kernel parameter block (plain data, passed by value)
@@ -244,7 +272,7 @@ struct Cfg {
   static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV
       : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || PAIR)) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
-  // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau ; padded to even
+  // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau (fp32: tau_hi, tau_lo) ; padded to even
   //          (pair) V[NC], tau (flag 3 only), pad to QOFF, then A_c*(cos,sin) of the TW/2 pair offsets for
   //          every component c: [QOFF + 2(p*NC + c)]; padded to a multiple of 4 (16-byte rows in fp32)
   // fp64 pair kernel on the FP64 tensor cores (DMMA.8x8x4, srb_pair.cuh): the accumulation is a GEMM
@@ -260,7 +288,8 @@ struct Cfg {
   static constexpr int NREC_FLUSH = MMA ? (((32 * NACC - 16 - NSEED * 33 + 31) / 32 + 3) & ~3) : 0;
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
       : PAIR ? (NREC_PAIR > NREC_FLUSH ? NREC_PAIR : NREC_FLUSH)
-      : (((NV + (KIND_ == KIND_RECUR ? 3 : 1)) + 1) & ~1);
+      : (((NV + (KIND_ == KIND_RECUR ? 3 : (sizeof(TM_) == 4 ? 2 : 1))) + 1) & ~1);   // direct, fp32: tau as hi + lo
+  using TW_T = typename std::conditional<KIND_ == KIND_DIRECT, double, TM_>::type;      // type of the lane's omega nodes
 };
 
 template <class C>
@@ -273,7 +302,7 @@ struct WarpSmem {
 template <class C>
 struct ThreadState {
   typename C::TM acc[C::NACC];
-  typename C::TM wl[(C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) ? C::TW : 1];   // this lane's omega nodes
+  typename C::TW_T wl[(C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) ? C::TW : 1];   // this lane's omega nodes
   typename C::TM pprev[C::KIND == KIND_LITERAL ? C::TW : 1];   // literal kind: per-node phasePrev
   typename C::TM ff[C::KIND == KIND_LITERAL ? C::TW : 1];      // literal kind: per-node FormFactor
   unsigned long long nPass, nAll;
@@ -514,6 +543,8 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
   if (!C::PAIR || flag == 3u)
     sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau ; pair: flag 3 only
+  if (C::KIND == KIND_DIRECT && sizeof(TM) == 4)
+    sm.rec[lane][C::NV + 1] = (TM)ssub(tau, (double)(TM)tau);   // fp32 direct: tau = hi + lo (48 bits)
   if (C::KIND == KIND_RECUR) { sm.rec[lane][C::NV + 1] = (TM)last[1]; sm.rec[lane][C::NV + 2] = (TM)last[2]; }
   return flag;
 }
@@ -620,11 +651,12 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
 
 // Direct main phase: lane = tile of TW nodes, per-node sincos of the reference's rounded phase.
 template <class C>
-SRB_HD void direct_update(const typename C::TM* V, typename C::TM w, typename C::TM tau, int k, ThreadState<C>& st) {
+SRB_HD void direct_update(const typename C::TM* V, double w_, double tau, int k, ThreadState<C>& st) {
   using TM = typename C::TM;
   TM sn, cs;
-  const TM ph = tmul(w, tau);  // single rounding == the reference's omega*(time - n.r)
-  if (C::NATIVE) sincos_native((float)ph, (float*)&sn, (float*)&cs); else sincos_t(ph, &sn, &cs);
+  const TM w = (TM)w_;
+  if constexpr (sizeof(TM) == 4) sincos_mixed<C::NATIVE>(w_, tau, (float*)&sn, (float*)&cs);
+  else sincos_t(smul(w_, tau), &sn, &cs);  // single rounding == the reference's omega*(time - n.r)
   if (C::MODE == MODE_FAR) {
 #pragma unroll
     for (int c = 0; c < C::NC; c++) {
@@ -653,7 +685,7 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
       TM V[NV];
 #pragma unroll
       for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
-      const TM tau = sm.rec[s][NV];
+      const double tau = sizeof(TM) == 4 ? (double)sm.rec[s][NV] + (double)sm.rec[s][NV + 1] : (double)sm.rec[s][NV];
 #pragma unroll
       for (int k = 0; k < TW; k++) direct_update<C>(V, st.wl[k], tau, k, st);
     }
@@ -667,7 +699,7 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
     TM V[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
-    const TM tau = sm.rec[s][NV];
+    const double tau = sizeof(TM) == 4 ? (double)sm.rec[s][NV] + (double)sm.rec[s][NV + 1] : (double)sm.rec[s][NV];
     const int kmin = tile_lo((int)(r & 0x3ffu), 31, 32), kmax = tile_lo((int)((r >> 10) & 0x3ffu), 0, 32);   // warp-uniform
 #pragma unroll
     for (int k = 0; k < TW; k++) {
@@ -836,7 +868,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
 #pragma unroll
       for (int k = 0; k < C::TW; k++) {
         const uint32_t j = g.cLo + (uint32_t)(lane + 32 * k);
-        SRB_ST.wl[k] = j < g.cHi ? (TM)((const TI*)P.omega)[j] : (TM)0;
+        SRB_ST.wl[k] = j < g.cHi ? (typename C::TW_T)((const TI*)P.omega)[j] : (typename C::TW_T)0;
         if (C::KIND == KIND_LITERAL)
           SRB_ST.ff[k] = (j < g.cHi && P.formFactor) ? (TM)((const TI*)P.formFactor)[j] : (TM)1;
       }

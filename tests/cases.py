@@ -177,3 +177,63 @@ def betatron_args(info, grid=(256, 32, 32), dtype='double'):
     wc = info['omega_crit_1m']
     return {"grid": [(1e-3 * wc, wc), (0, 2 * info['K0'] / info['gamma0']), (0.0, 2 * np.pi), tuple(grid)],
             "dtype": dtype, "ctx": [0, 0]}
+
+
+def spiral_tracks(Np=10000, seed=0, N_winds=1, L_b=0.4e-6, energy_MeV=100.0, n_p=5e24, K0=4.0, Num_osc=3,
+                  samples_per_osc=64, energy_spread=0.001, pr_spread=0.0, substeps=16):
+    """C4 (BASELINE configs[3]): the spiral beam of tutorials/Spiral_Beam_Part1.ipynb:56-75 (cells 2-3:
+    100 MeV, n_p = 5e24 m^-3, K0 = 4, one spiral winding over 0.4 um, 3 channel oscillations x 64 samples = 192
+    samples) in SI units, seeded.  The notebook integrates each particle with scipy's Radau solver (cell 4); the
+    tracks here come from a deterministic vectorised kick-drift leap-frog of the same equations of motion
+    (momenta at t_k, coordinates staggered by dt/2 as the notebook stores them) -- parity needs identical inputs
+    on both sides, not the notebook's integrator.  Returns (tracks, c*dt, info)."""
+    from scipy.constants import c, e, m_e, physical_constants
+    r_e = physical_constants['classical electron radius'][0]
+    rs = np.random.RandomState(seed)
+    g0 = energy_MeV * 1e6 * e / (m_e * c ** 2)
+    pz0 = (g0 ** 2 - K0 ** 2 - 1) ** .5
+    w_p = c * (4 * np.pi * r_e * n_p) ** 0.5
+    w_ch = w_p / (2 * g0) ** 0.5
+    R_match = K0 * c / w_p * (2 / g0) ** 0.5
+    lam_ch = 2 * np.pi * c / w_ch
+    w_crit = 1.5 * K0 * g0 ** 2 * w_ch
+    k_sp = 2 * np.pi / (L_b / N_winds)
+    beta_phs = pz0 / g0 + w_ch / (k_sp * c)
+    theta_vc = float(np.arccos(1 / beta_phs))
+    theta_beta = K0 / g0
+    T_fin = Num_osc * lam_ch / c
+    Nt = int(Num_osc * samples_per_osc)
+    dt = T_fin / (Nt - 1)
+    z = np.linspace(0, L_b, Np)
+    if Np > 1:
+        z = z + 0.5 * (z[1] - z[0]) * (rs.rand(Np) - 0.5)
+    x = R_match * np.sin(k_sp * z); y = R_match * np.cos(k_sp * z)
+    ux = -K0 * np.cos(k_sp * z) * (1 + pr_spread * rs.randn(Np))
+    uy = K0 * np.sin(k_sp * z) * (1 + pr_spread * rs.randn(Np))
+    uz = pz0 * (1 + energy_spread * rs.randn(Np))
+    X = np.empty((6, Np, Nt))
+    h = dt / substeps
+    k = 0.5 * w_p ** 2 / c
+    gam = np.sqrt(1 + ux ** 2 + uy ** 2 + uz ** 2)
+    xs, ys, zs = x + 0.5 * h * c * ux / gam, y + 0.5 * h * c * uy / gam, z + 0.5 * h * c * uz / gam
+    for it in range(Nt):
+        X[3, :, it], X[4, :, it], X[5, :, it] = ux, uy, uz
+        for s in range(substeps):
+            if s == substeps // 2:
+                X[0, :, it], X[1, :, it], X[2, :, it] = (xs - 0.5 * h * c * ux / gam, ys - 0.5 * h * c * uy / gam,
+                                                       zs - 0.5 * h * c * uz / gam)
+            ux = ux - h * k * xs; uy = uy - h * k * ys
+            gam = np.sqrt(1 + ux ** 2 + uy ** 2 + uz ** 2)
+            xs = xs + h * c * ux / gam; ys = ys + h * c * uy / gam; zs = zs + h * c * uz / gam
+    tracks = [[X[0, i].copy(), X[1, i].copy(), X[2, i].copy(), X[3, i].copy(), X[4, i].copy(), X[5, i].copy(), 1.0, 0]
+              for i in range(Np)]
+    info = dict(K0=K0, gamma0=g0, omega_crit_1m=w_crit / (2 * np.pi * c), theta_vc=theta_vc, theta_beta=theta_beta,
+                L_b=L_b)
+    return tracks, c * dt, info
+
+
+def spiral_args(info, grid=(512, 64, 64), dtype='float'):
+    """Grid of tutorials/Spiral_Beam_Part1.ipynb:255-264 (cell 6) at the BASELINE C4 node counts."""
+    th_max = 1.2 * max(info['theta_beta'], info['theta_vc'])
+    return {"grid": [(1., 3 * info['omega_crit_1m']), (0, th_max), (0.0, 2 * np.pi), tuple(grid)],
+            "dtype": dtype, "ctx": [0, 0]}

@@ -103,7 +103,54 @@ def file_flow_case(rr):
     return args, tr, dt, res, stored
 
 
+def c4_cases():
+    """BASELINE configs[3] (spiral beam, tutorials/Spiral_Beam_Part1.ipynb) at a size the CPU reference finishes in
+    seconds: a 200-particle spiral of the same recipe on a coarser grid, with the notebook's two calls (:255-274:
+    incoherent `total`, coherent `cartesian_complex`) in the config's single precision and in double, plus the
+    coherent call with a particle form factor.  name -> (args, tracks, dt, kwargs)."""
+    tr, dt, info = cases.spiral_tracks(200, seed=0)
+    out = {}
+    out['c4_float_total'] = (cases.spiral_args(info, grid=(128, 8, 8), dtype='float'), tr, dt, dict(Np_max=100))
+    out['c4_double_total'] = (cases.spiral_args(info, grid=(128, 8, 8), dtype='double'), tr, dt, dict(Np_max=100))
+    out['c4_double_coherent'] = (cases.spiral_args(info, grid=(128, 8, 8), dtype='double'), tr, dt,
+                                 dict(comp='cartesian_complex'))
+    out['c4_double_coherent_sigma'] = (cases.spiral_args(info, grid=(96, 6, 5), dtype='double'), tr, dt,
+                                       dict(comp='cartesian_complex', sigma_particle=1e-10))
+    out['c4_float_coherent'] = (cases.spiral_args(info, grid=(96, 6, 5), dtype='float'), tr, dt,
+                                dict(comp='cartesian_complex'))
+    return out
+
+
+C4_POST = [('get_energy', dict(normalize_to_weights=True, lambda0_um=1e6)),      # Spiral_Beam_Part1.ipynb:283-284
+           ('get_energy_spectrum', dict(normalize_to_weights=True))]
+
+
+def main_c4():
+    """Writes reference_c4.npz / reference_c4_meta.json (kept apart from reference_cases.npz so that adding the C4
+    recipe does not rewrite the round-1 vectors)."""
+    from oracle import run_reference as rr
+    assert rr.available(), 'needs /root/reference'
+    blobs, meta = {}, {}
+    for name, (args, tracks, dt, kw) in c4_cases().items():
+        res = rr.run(args, tracks, timeStep=dt, post=C4_POST, **kw)
+        for key, arr in res['radiation'].items():
+            blobs[f'{name}/{key}'] = arr
+        for i, v in res['post'].items():
+            blobs[f'{name}/post{i}'] = np.asarray(v)
+        meta[name] = dict(total_weight=res['total_weight'], keys=list(res['radiation']))
+        print(name, 'ok', {k: v.shape for k, v in res['radiation'].items()}, float(res['post'][0]))
+    # "Enhancement due to coherency" as the notebook prints it (:283-287), from the reference's own utils.py
+    meta['_coherent_gain_double'] = float(blobs['c4_double_coherent/post0'] / blobs['c4_double_total/post0'])
+    meta['_device'] = res['device']
+    print('coherent gain', meta['_coherent_gain_double'])
+    np.savez_compressed(os.path.join(HERE, 'reference_c4.npz'), **blobs)
+    with open(os.path.join(HERE, 'reference_c4_meta.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+
+
 def main():
+    if '--c4' in sys.argv:
+        return main_c4()
     from oracle import run_reference as rr
     assert rr.available(), 'needs /root/reference'
     blobs, meta = {}, {}

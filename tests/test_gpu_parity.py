@@ -3,9 +3,11 @@ the CPU oracle and the committed golden fixtures.
 
 Tolerances (BASELINE.json north_star):
   double : max|d|/max|ref| <= 1e-9 and ||d||2/||ref||2 <= 1e-9 against the strict oracle
-  single : mixed-precision kernel; accepted when it is no further from the fp64 oracle than the
-           literal fp32 restatement and within 2e-4 norm-wise of the fp64 oracle, integrated
-           energy within 1e-4 (fp32 protocol of SURVEY §7)
+  single : mixed-precision kernels; accepted when no further from the fp64 oracle than the literal fp32
+           restatement and within 1e-4 norm-wise of the fp64 oracle (north_star's single-precision tolerance;
+           measured ~2e-6 for every kernel since the direct kernel forms and reduces its phase in fp64),
+           integrated energy within 1e-4 (fp32 protocol of SURVEY §7); `float_mode='literal'` against the
+           reference's fp32 output: 1e-4
 """
 import ctypes
 import json
@@ -315,7 +317,7 @@ def test_float_modes_protocol(cuda_lib, oracle):
         calc = run_gpu(a, tracks, dt, phasor=phasor)
         e = rel_errors(calc.Data['radiation']['total'], r64['radiation']['total'])
         assert e[0] <= e_lit[0] and e[1] <= e_lit[1], (phasor, native, e, e_lit)
-        assert max(e) <= 2e-4, (phasor, native, e)
+        assert max(e) <= 1e-4, (phasor, native, e)
         assert abs(calc.get_energy(lambda0_um=1) - E64) / E64 < 1e-4
 
 

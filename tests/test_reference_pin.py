@@ -305,3 +305,48 @@ def test_product_args_equal_the_reference_args(ref_gold, name):
         if key in ('omega', 'theta', 'phi', 'radius', 'sigma_particle', 'timeStep', 'wavelengths'):
             if not (key == 'theta' and A['mode'] == 'near'):
                 assert got.dtype == want.dtype, (name, key, got.dtype, want.dtype)
+
+
+# ------------------------------------------------------------------------------- BASELINE configs[3] (C4, spiral beam)
+from golden.make_reference_golden import C4_POST, c4_cases  # noqa: E402
+
+C4 = c4_cases()
+
+
+@pytest.fixture(scope='module')
+def c4_gold():
+    return (np.load(os.path.join(GOLD, 'reference_c4.npz')), json.load(open(os.path.join(GOLD, 'reference_c4_meta.json'))))
+
+
+@pytest.mark.parametrize('name', sorted(C4))
+def test_oracle_is_bit_identical_to_the_reference_on_c4(oracle, c4_gold, name):
+    """The spiral-beam recipe of tutorials/Spiral_Beam_Part1.ipynb (SI units, single and double precision, the
+    notebook's incoherent `total` and coherent `cartesian_complex` calls): oracle == unmodified reference, bit for bit."""
+    stored, meta = c4_gold
+    args, tracks, dt, kw = C4[name]
+    res = oracle.calculate_spectrum(args, tracks, dt, **kw)
+    assert list(res['radiation']) == meta[name]['keys']
+    for key, arr in res['radiation'].items():
+        assert np.array_equal(arr, stored[f'{name}/{key}']), (name, key, rel_errors(arr, stored[f'{name}/{key}']))
+    assert res['total_weight'] == meta[name]['total_weight']
+    for i, (meth, pkw) in enumerate(C4_POST):
+        np.testing.assert_allclose(getattr(oracle, meth)(res, **pkw), stored[f'{name}/post{i}'], rtol=1e-13, atol=0)
+
+
+def test_c4_coherent_gain_of_the_reference(oracle, c4_gold):
+    """'Enhancement due to coherency' (Spiral_Beam_Part1.ipynb:283-287) of the stored reference run, recomputed by the
+    oracle's restated utils integrals."""
+    stored, meta = c4_gold
+    e = {}
+    for name in ('c4_double_coherent', 'c4_double_total'):
+        args, tracks, dt, kw = C4[name]
+        e[name] = oracle.get_energy(oracle.calculate_spectrum(args, tracks, dt, **kw), **C4_POST[0][1])
+    assert e['c4_double_coherent'] / e['c4_double_total'] == pytest.approx(meta['_coherent_gain_double'], rel=1e-12)
+
+
+@needs_reference
+def test_live_reference_reproduces_c4(c4_gold):
+    stored, _ = c4_gold
+    args, tracks, dt, kw = C4['c4_float_total']
+    res = run_reference.run(args, tracks, timeStep=dt, **kw)
+    assert np.array_equal(res['radiation']['total'], stored['c4_float_total/total'])
