@@ -153,8 +153,11 @@ class SynchRad(Utilities):
         if self.plat_name == 'None':
             raise RuntimeError('this SynchRad object was created without a device (ctx=False)')
         from . import engine
+        import time
         import torch
         track_source = None
+        t_call = time.perf_counter()
+        t_open = t_pack = 0.0
 
         if comp not in host.COMP_KEYS:
             raise ValueError(f'unknown comp {comp!r}')
@@ -178,6 +181,8 @@ class SynchRad(Utilities):
 
         if file_tracks is not None:
             from . import trackio
+            t0 = time.perf_counter()
+            trackio.read_seconds = 0.0
             cdt, file_range, n_file = trackio.read_header(file_tracks)
             self.Args['timeStep'] = self.dtype(cdt)
             self._timeStep64 = float(cdt)
@@ -193,6 +198,7 @@ class SynchRad(Utilities):
             # batches are packed below (the reference holds every local track in host RAM, calc.py:210-216)
             track_source = trackio.TrackSource(file_tracks, index)
             particleTracks = track_source.tracks
+            t_open = time.perf_counter() - t0
             if self.rank == 0 and verbose:
                 print('Tracks are loaded')
         elif isinstance(particleTracks, host.PackedTracks):
@@ -237,9 +243,11 @@ class SynchRad(Utilities):
         try:
             for b in batches:
                 if isinstance(b, tuple):
+                    t0 = time.perf_counter()
                     alloc = engine.PinnedAlloc()
                     packed = host.pack_tracks(particleTracks[b[0]:b[1]], weights[b[0]:b[1]], np.double, it_range,
                                               nSnaps, alloc)
+                    t_pack += time.perf_counter() - t0
                 res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
                                        spectra=None if res is None else res.spectra,
                                        counters_into=None if res is None else res.counters, **run)
@@ -274,6 +282,11 @@ class SynchRad(Utilities):
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
             'h2d_bytes': h2d,
             'd2h_bytes': int(sum(v.nbytes for v in self.Data['radiation'].values())),
+            # host-side seconds of this call: opening the tracks file (headers of every track), packing the tracks
+            # into the pinned SoA buffers (of which reading the samples out of the file), everything else up to here
+            'file_open_s': t_open, 'host_pack_s': t_pack,
+            'file_read_s': float(trackio.read_seconds) if file_tracks is not None else 0.0,
+            'total_s': time.perf_counter() - t_call,
         }
 
         if file_spectrum is not None and self.rank == 0:

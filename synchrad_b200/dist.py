@@ -13,6 +13,9 @@ def reduce_to_root(comm, tensors, total_weight, counters=None):
     Returns (tensors, total_weight, counters) as seen by this rank after the reduction."""
     rank = comm.get_rank()
     buf = torch.stack(tensors)
+    dev = buf.device
+    if comm.get_backend() == 'gloo' and buf.is_cuda:      # ranks sharing one GPU (tests): gloo reduces host tensors
+        buf = buf.cpu()
     comm.reduce(buf, dst=0, op=comm.ReduceOp.SUM)
     n_cnt = 0 if counters is None else counters.numel()
     scal = torch.zeros(1 + n_cnt, dtype=torch.float64, device=buf.device)
@@ -21,7 +24,7 @@ def reduce_to_root(comm, tensors, total_weight, counters=None):
         scal[1:] = counters.to(torch.float64)       # exact below 2^53
     comm.reduce(scal, dst=0, op=comm.ReduceOp.SUM)
     if rank == 0:
-        out = list(buf.unbind(0))
+        out = list(buf.to(dev).unbind(0))
         tw = float(scal[0].item())
         cnt = scal[1:].to(torch.int64) if counters is not None else None
     else:

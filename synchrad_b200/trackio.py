@@ -12,6 +12,8 @@ spectrum file (calc.py:274-290 written, :648-666 read):
 h5py is used when it is importable; otherwise the bundled minimal reader/writer (h5lite) handles
 exactly these layouts.
 """
+import time as _time
+
 import numpy as np
 
 try:                                   # pragma: no cover - not installed in the build image
@@ -22,6 +24,9 @@ except ImportError:
     BACKEND = 'h5lite'
 
 _COMPS = ('x', 'y', 'z', 'ux', 'uy', 'uz')
+
+# seconds spent reading samples out of tracks files (FileTrack.read_into); reset and read by calc.calculate_spectrum
+read_seconds = 0.0
 
 
 def read_header(path):
@@ -79,7 +84,10 @@ class FileTrack:
         raise IndexError(k)
 
     def read_into(self, c, dest):
+        global read_seconds
+        t0 = _time.perf_counter()
         self._g[_COMPS[c]].read_direct(dest)
+        read_seconds += _time.perf_counter() - t0
 
 
 class TrackSource:
