@@ -45,6 +45,13 @@ GRID = (256, 32, 32)
 KIND_NAMES = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair, DFMA'}
 
 
+def kernel_label(info, fp64):
+    """k_integrate<...> as reported by srb_last_launch: the fp64 pair kernel runs on DMMA when tile width x components % 8 == 0"""
+    kind, tw, nc = int(info.kind), int(info.tile_width), int(info.n_components)
+    name = 'pair, DMMA' if (kind == 3 and fp64 and (tw * nc) % 8 == 0) else KIND_NAMES[kind]
+    return 'k_integrate<%s, tile %d>' % (name, tw)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -327,7 +334,7 @@ def run_product(a):
             upd32 = np32 * (n_s - 1) * nodes
             rate = upd32 / (k_ms32 * 1e-3)
             fp32[mode] = {
-                'value': rate, 'unit': 'updates/s', 'kernel': 'k_integrate<%s, tile %d>' % (KIND_NAMES[int(res32.info.kind)], res32.info.tile_width),
+                'value': rate, 'unit': 'updates/s', 'kernel': kernel_label(res32.info, False),
                 'what': {'mixed': "dtype='float' default: fp64 tracks/tables/per-step work, fp32 per-omega phasor + accumulate "
                                   '(judged against the fp64 oracle, <= 1e-4)',
                          'literal': "dtype='float', float_mode='literal': every operation of the reference kernels in fp32 "
@@ -371,7 +378,7 @@ def run_product(a):
                   'checker_port_bit_identical_to_reference_kernels': bool(np.array_equal(port['radiation']['total'], want)),
                   'checker': strict_lib + (' (the reference\'s own kernels, g++ -O2 -ffp-contract=off)' if strict_lib == 'ref_strict'
                                            else ' (oracle port, strict build)'),
-                  'kernel': 'k_integrate<%s, tile %d>' % (KIND_NAMES[int(resp.info.kind)], resp.info.tile_width),
+                  'kernel': kernel_label(resp.info, a.dtype == 'double'),
                   'sample': f'{npar} particle(s) x {n_s} samples x {GRID[0]}x{GRID[1]}x{GRID[2]} nodes = the CPU arm\'s first '
                             f'particles, full bench shape, phasor={a.phasor}; checker {dt_strict:.1f} s'}
         del resp, dbatch
@@ -461,9 +468,8 @@ def run_product(a):
         issued = 2.0 * ((tw - 2) + nc * tw + 2) / tw
     elif int(info.kind) in (3, 4):   # pair: per lane and step 4 (X = Y*Z) + 4*NC*TW/2 accumulate FMAs, for TW updates;
         issued = (4 + 2 * nc * tw) / tw   # fp64 with TW*NC % 8 == 0: the accumulate FMAs are issued as DMMA.8x8x4 (256 each)
-    mma = int(info.kind) == 3 and a.dtype == 'double' and (tw * nc) % 8 == 0
-    kname = 'pair, DMMA' if mma else KIND_NAMES[int(info.kind)]
-    kernel_name = 'k_integrate<%s, tile %d>' % (kname, info.tile_width)
+    kernel_name = kernel_label(info, a.dtype == 'double')
+    kname = kernel_name[len('k_integrate<'):].rsplit(',', 1)[0]
     ev, ev_src = ncu_evidence(kernel_name, n_p, n_s)
     roofline = {
         'bound': 'fp64_pipe' if a.dtype == 'double' else 'fp32_pipe',
