@@ -13,6 +13,7 @@
 
 #include "../../include/synchrad_b200.h"
 #include "srb_literal.cuh"
+#include "srb_ws.cuh"
 
 namespace {
 
@@ -66,10 +67,227 @@ __global__ void __launch_bounds__(NW * 32, min_blocks<C>()) k_integrate(const sr
   srb::warp_task<C>(P, vd, pc, *sm, &st);
 }
 
+// ------------------------------------------------------------------------------------------- warp-specialised pair kernel
+// (srb_ws.cuh: 1 DMMA consumer warp + NP producer warps per virtual direction, NU directions per block, mbarrier ring,
+//  TMA-staged inputs)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (both addresses and the size 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class C, int NU, int NP, int NS>
+struct alignas(128) WsSmem {
+  srb::WsStage<C> stage[NU][NS];
+  double in[NU][NP][srb::WS_IN][srb::WS_NIN];        // TMA-staged input records of a producer's next sub-batch
+  uint64_t full[NU][NS], empty[NU][NS], inbar[NU][NP], xfer[NU][NS];
+};
+
+// NCW consumer warps per unit.  With two, the sub-batches alternate between them (a split of the GEMM's K dimension:
+// each holds a full accumulator set) so that one warp's LDS / rotation / bookkeeping instructions issue under the
+// other's 16-cycle DMMA issue stalls; at a flush the second warp hands its sums to the first through the stage.
+template <class C, int NU, int NP, int NS, int NCW>
+__global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const srb::Params P) {
+  using namespace srb;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  WsSmem<C, NU, NP, NS>& S = *reinterpret_cast<WsSmem<C, NU, NP, NS>*>(smraw);
+  static_assert(sizeof(WsStage<C>) >= 32 * C::NACC * sizeof(double), "stage too small for the flush transposes");
+  static_assert(sizeof(WsStage<C>) % 16 == 0, "stages keep the input rows 16-byte aligned");
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+  // masked steps of the tensor-core stream multiply stale stage data by 0: keep it finite from the start
+  for (uint32_t k = threadIdx.x; k < sizeof(S.stage) / 4u; k += blockDim.x) reinterpret_cast<uint32_t*>(&S.stage)[k] = 0u;
+  if (threadIdx.x == 0) {
+    for (int u = 0; u < NU; u++) {
+      for (int i = 0; i < NS; i++) { mbar_init(&S.full[u][i], 32); mbar_init(&S.empty[u][i], 32); mbar_init(&S.xfer[u][i], 32); }
+      for (int q = 0; q < NP; q++) mbar_init(&S.inbar[u][q], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const bool consumer = warp < NCW * NU;
+  const int u = warp % NU;                                       // (warp w sits on sub-partition w % 4: one unit each)
+  const int cidx = consumer ? warp / NU : 0;
+  const int pidx = consumer ? 0 : (warp - NCW * NU) / NU;
+  const uint32_t nVDtiles = (P.nVD + NU - 1) / NU;
+  const uint32_t vd = (blockIdx.x % nVDtiles) * NU + (uint32_t)u;   // neighbouring blocks share the tracks
+  const uint32_t pc = blockIdx.x / nVDtiles;
+  if (vd >= P.nVD) return;
+  Geom g;
+  make_geom<C>(P, vd, g);
+  uint32_t t0, t1;
+  chunk_tracks(P, pc, t0, t1);
+  Walk<C> w;
+  w.init(t0, t1);
+  WalkItem it;
+  uint32_t k = 0;
+
+  if (consumer) {
+    ThreadState<C> st;
+    uint32_t xph = 0u;                 // per-stage phase bits of the hand-over barriers (a stage cannot be handed over
+    while (w.next(P, it)) {             // twice before warp 0 has released it, so its barrier never runs ahead)
+      const int sgi = (int)(k % (uint32_t)NS);
+      const uint32_t par = (k / (uint32_t)NS) & 1u;
+      if (it.newTrack) {
+#pragma unroll
+        for (int q = 0; q < C::NACC; q++) st.acc[q] = 0.0;
+      }
+      WsStage<C>& sg = S.stage[u][sgi];
+      if (it.kind == 0) {
+        if ((int)(k % (uint32_t)NCW) == cidx) {
+          mbar_wait(&S.full[u][sgi], par);
+          ws_main<C>(P, g, sg, lane, st);
+          mbar_arrive(&S.empty[u][sgi]);
+        }
+      } else {
+        mbar_wait(&S.full[u][sgi], par);
+        double* buf = reinterpret_cast<double*>(&sg);
+        if (NCW > 1 && cidx == 1) {
+          // hand this warp's sums to warp 0 (same fragment layout, lane-major) and restart from zero: warp 0 carries
+          // the cumulative amplitude from here on (snapshots are cumulative)
+#pragma unroll
+          for (int q = 0; q < C::NACC; q++) { buf[q * 32 + lane] = st.acc[q]; st.acc[q] = 0.0; }
+          mbar_arrive(&S.xfer[u][sgi]);
+        } else {
+          if (NCW > 1) {
+            mbar_wait(&S.xfer[u][sgi], (xph >> sgi) & 1u);
+            xph ^= 1u << sgi;
+#pragma unroll
+            for (int q = 0; q < C::NACC; q++) st.acc[q] += buf[q * 32 + lane];
+            __syncwarp();
+          }
+          // flush: fragment layout -> one tile per lane (through the handed-over stage), common flush code, and back
+          ws_store_frag<C>(buf, lane, st);
+          __syncwarp();
+          ws_load_tile<C>(buf, lane, st);
+          flush_lane<C>(P, g, w.tv, pc, it.iSnap, lane, &st);
+          ws_store_tile<C>(buf, lane, st);
+          __syncwarp();
+          ws_load_frag<C>(buf, lane, st);
+          __syncwarp();
+          mbar_arrive(&S.empty[u][sgi]);
+        }
+      }
+      k++;
+    }
+    return;
+  }
+
+  // ---- producer pidx of unit u: items k with k % NP == pidx
+  struct Own { uint32_t kind, base, k, itStart; int cnt; uint64_t idx; bool valid; };   // idx: element of step `base` in the arrays
+  auto next_own = [&](Own& o) {
+    while (w.next(P, it)) {
+      const uint32_t kk = k++;
+      if (kk % (uint32_t)NP == (uint32_t)pidx) {
+        o.kind = it.kind; o.base = it.base; o.cnt = it.cnt; o.k = kk; o.itStart = w.tv.itStart;
+        o.idx = (uint64_t)((const double*)w.tv.x - (const double*)P.x) + it.base;
+        o.valid = true;
+        return;
+      }
+    }
+    o.valid = false;
+  };
+  const uint64_t totalSteps = P.offsets[P.nTracks];
+  // Staged inputs of the sub-batch whose first step is element idx: the 34 packed records (k_prepass: x, y, z, a, b per
+  // step, 72 bytes) from the even index at or below idx - 1 (previous step + 16-byte alignment), ONE bulk copy.
+  // Sub-batches at the edges of the arrays use plain loads.
+  auto can_tma = [&](const Own& o) -> bool { return P.tmaOK && o.idx >= 2 && o.idx + 33 <= totalSteps; };
+  auto issue = [&](const Own& o) {
+    __syncwarp();                       // every lane has consumed the previous sub-batch's inputs
+    if (lane == 0 && can_tma(o)) {
+      uint64_t* bar = &S.inbar[u][pidx];
+      const uint64_t e0 = (o.idx - 1) & ~(uint64_t)1;
+      mbar_arrive_expect_tx(bar, (uint32_t)(WS_NIN * WS_IN * 8));
+      tma_load_1d(&S.in[u][pidx][0][0], P.pre + e0 * WS_NIN, (uint32_t)(WS_NIN * WS_IN * 8), bar);
+    }
+  };
+  WsConst kc;
+  ws_const<C>(P, g, kc);
+  unsigned long long nPass = 0, nAll = 0;
+  Own cur, nxt;
+  uint32_t inphase = 0u;
+  next_own(cur);
+  if (cur.valid && cur.kind == 0) issue(cur);
+  while (cur.valid) {
+    next_own(nxt);
+    const int sgi = (int)(cur.k % (uint32_t)NS);
+    mbar_wait(&S.empty[u][sgi], ((cur.k / (uint32_t)NS) & 1u) ^ 1u);
+    WsStage<C>& sg = S.stage[u][sgi];
+#if defined(SRB_WS_FAKE_PRODUCER)      // tuning aid: stages are filled once, then only handed over (consumer-only timing)
+    if (cur.kind == 0 && cur.k >= (uint32_t)(2 * NS * NP)) { mbar_arrive(&S.full[u][sgi]); cur = nxt; continue; }
+#endif
+    if (cur.kind == 0) {
+      const uint32_t itl = cur.base + (uint32_t)lane;
+      const bool active = lane < cur.cnt;
+      double x, y, z, a[3], b[3], xp = 0, yp = 0, zp = 0;
+      if (can_tma(cur)) {
+        mbar_wait(&S.inbar[u][pidx], inphase);
+        inphase ^= 1u;
+        const double (*in)[WS_NIN] = S.in[u][pidx];
+        const int sl = (int)(cur.idx - ((cur.idx - 1) & ~(uint64_t)1)) + lane;      // 1 or 2, + lane
+        x = in[sl][0]; y = in[sl][1]; z = in[sl][2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { a[c] = in[sl][3 + c]; b[c] = in[sl][6 + c]; }
+        if (lane == 0) { xp = in[sl - 1][0]; yp = in[sl - 1][1]; zp = in[sl - 1][2]; }
+      } else {                          // edge of the arrays: plain loads
+        x = y = z = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[c] = b[c] = 0.0;
+        const uint64_t e = cur.idx + (uint64_t)lane;
+        if (active) {
+          const double* q = P.pre + e * WS_NIN;
+          x = q[0]; y = q[1]; z = q[2];
+#pragma unroll
+          for (int c = 0; c < 3; c++) { a[c] = q[3 + c]; b[c] = q[6 + c]; }
+        }
+        if (lane == 0 && itl > 0) { const double* q = P.pre + (e - 1) * WS_NIN; xp = q[0]; yp = q[1]; zp = q[2]; }
+      }
+      // tau = t - n.r in the reference's operation order (kernel_farfield.cl:65-67); the previous step's tau from the
+      // neighbouring lane, lane 0 recomputes it (0 for it == 0: phasePrev starts at 0, Q1)
+      const double tau = ssub(smul((double)(cur.itStart + itl), P.dt), sdot3(x, y, z, g.nx, g.ny, g.nz));
+      double tauPrev = __shfl_up_sync(0xffffffffu, tau, 1);
+      if (lane == 0)
+        tauPrev = itl == 0 ? 0.0 : ssub(smul((double)(cur.itStart + itl - 1), P.dt), sdot3(xp, yp, zp, g.nx, g.ny, g.nz));
+      WsStep ws;
+      ws_prep_guard<C>(P, g, kc, active, tau, tauPrev, a, b, ws, nPass, nAll);
+      // Every staged input has been CONSUMED by now (tau, tauPrev, the amplitude), not merely requested: a shared-memory
+      // load still queued in the LSU could be overtaken by the TMA engine's write (seen as a ~1e-8 run-to-run wobble
+      // of the spectrum when the copy was issued right after the loads).  The single input buffer is free for this
+      // producer's next sub-batch, whose copies then have the phasor part of this item (~2/3 of it) to land.
+      if (nxt.valid && nxt.kind == 0) issue(nxt);
+      const uint32_t fl = ws_prep_store<C>(P, kc, ws, sg, lane);
+      const uint32_t fullMask = __ballot_sync(0xffffffffu, fl == 1u);
+      const uint32_t anyMask = __ballot_sync(0xffffffffu, fl != 0u);
+      if (lane == 0) { sg.cnt = (uint32_t)cur.cnt; sg.fullMask = fullMask; sg.anyMask = anyMask; }
+    } else if (nxt.valid && nxt.kind == 0) {
+      issue(nxt);                       // flush item: nothing to read, the buffer is free
+    }
+    mbar_arrive(&S.full[u][sgi]);
+    cur = nxt;
+  }
+  if (P.counters && nAll) { atomicAdd(P.counters, nPass); atomicAdd(P.counters + 1, nAll); }
+}
+
 // Direction-independent per-step kinematics, once per call (instead of once per direction):
 // far: a = (beta_{it+1}-beta_it)/dt and b = (beta_{it+1}+beta_it)/2 ; near: beta_it.
 // Same strict operation order as the in-kernel path, so results are bit-identical.
-__global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_t total) {
+__global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_t total, uint64_t stride) {
   const double dtInv = srb::sdiv(1.0, P.dt);
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t a = 0, b = P.nTracks;          // last track with offsets[t] <= i
@@ -81,12 +299,20 @@ __global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_
       double av[3] = {0, 0, 0}, bv[3] = {0, 0, 0};
       if (it + 1 < n) srb::far_step_kinematics<double>(P.ux, P.uy, P.uz, i, dtInv, av, bv);
 #pragma unroll
-      for (int c = 0; c < 3; c++) { pre[c * total + i] = av[c]; pre[(3 + c) * total + i] = bv[c]; }
+      if (P.prePacked) {      // one record per step for the warp-specialised kernel: one TMA copy stages 34 steps
+        double* q = pre + i * 9;
+        q[0] = ((const double*)P.x)[i]; q[1] = ((const double*)P.y)[i]; q[2] = ((const double*)P.z)[i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { q[3 + c] = av[c]; q[6 + c] = bv[c]; }
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) { pre[c * stride + i] = av[c]; pre[(3 + c) * stride + i] = bv[c]; }
     } else {
       double bv[3];
       srb::near_step_kinematics<double>(P.ux, P.uy, P.uz, i, bv);
 #pragma unroll
-      for (int c = 0; c < 3; c++) pre[c * total + i] = bv[c];
+      for (int c = 0; c < 3; c++) pre[c * stride + i] = bv[c];
     }
   }
 }
@@ -216,10 +442,35 @@ struct Launcher {
   void (*kernel)(const srb::Params);
   size_t smem;
   int chunk;
+  int units;      // virtual directions per block
+  int threads;    // block size
 };
 
 template <class C> Launcher make_launcher() {
-  return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK};
+  return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK, NW, NW * 32};
+}
+template <class C, int NU, int NP, int NS, int NCW> Launcher make_launcher_ws() {
+  static_assert(sizeof(WsSmem<C, NU, NP, NS>) <= 227 * 1024, "ring does not fit the shared memory of an SM");
+  return Launcher{&k_integrate_ws<C, NU, NP, NS, NCW>, sizeof(WsSmem<C, NU, NP, NS>), C::CHUNK, NU, (NCW + NP) * NU * 32};
+}
+#ifndef SRB_WS_NP
+#define SRB_WS_NP 2     // producer warps per unit
+#endif
+#ifndef SRB_WS_NS
+#define SRB_WS_NS 4     // stages of a unit's ring
+#endif
+#ifndef SRB_WS_NCW
+#define SRB_WS_NCW 2    // DMMA consumer warps per unit
+#endif
+// warp-specialised form of the fp64 pair kernel on the tensor cores (tile width x components % 8 == 0); units per block
+// chosen so that the two-stage rings + input buffers fit the 227 KB of an SM
+bool pick_ws(int tw, int nc, Launcher* L) {
+  using srb::Cfg; using srb::KIND_PAIR; using srb::MODE_FAR;
+  if (tw == 8 && nc == 2) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 2>, 4, SRB_WS_NP, SRB_WS_NS, SRB_WS_NCW>(); return true; }
+  if (tw == 4 && nc == 2) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 4, false, 2>, 4, SRB_WS_NP, SRB_WS_NS, SRB_WS_NCW>(); return true; }
+  if (tw == 16 && nc == 2) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 16, false, 2>, 4, 2, 3, 1>(); return true; }
+  if (tw == 8 && nc == 3) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 3>, 4, SRB_WS_NP, 3, 1>(); return true; }
+  return false;
 }
 
 using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::KIND_PAIR_FMA; using srb::MODE_FAR; using srb::MODE_NEAR;
@@ -263,7 +514,7 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
 struct Plan {
   int kind, tw, nc;
   size_t preDoubles;      // doubles of scratch used by the per-step pre-pass (0 = computed in-kernel)
-  bool native;
+  bool native, ws;
   Launcher L;
   uint32_t chunkNodes, nChunks, nVD, nVDtiles, nPC;
   int blocksPerSM, numSM;
@@ -328,25 +579,45 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   if (g->phasor == SRB_PHASOR_PAIR_FMA && p->kind == KIND_PAIR && g->dtype == SRB_DTYPE_F64 && (p->tw * p->nc) % 8 == 0)
     p->kind = KIND_PAIR_FMA;
   if (!pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L)) return fail("internal: no kernel for this configuration");
-  p->chunkNodes = (uint32_t)p->L.chunk;
-  p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;
-  p->nVD = g->nPhi * g->nAxis2 * p->nChunks;
-  p->nVDtiles = (p->nVD + NW - 1) / NW;
-  p->nOut = srb_num_spectra(g->mode, g->comp);
-  p->perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
-  p->slabDoubles = p->perOut * p->nOut;
-  SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->L.smem));
-  SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, NW * 32, p->L.smem));
-  if (p->blocksPerSM < 1) return fail("kernel does not fit on an SM");
-  // particle chunks: fill whole waves of the machine; bounded by tracks, scratch and 64 waves
-  const uint64_t slots = (uint64_t)p->numSM * p->blocksPerSM;
-  uint64_t maxPC = t->nTracks ? t->nTracks : 1;
   // scratch = [pre-pass planes][private partial spectra]; the pre-pass is used when it fits
-  p->preDoubles = p->kind == KIND_LITERAL ? 0 : (size_t)(g->mode == SRB_MODE_FAR ? 6 : 3) * t->totalSteps_host;
+  // (plane stride rounded up to even: every plane starts 16-byte aligned, as the TMA staging of srb_ws.cuh wants)
+  p->preDoubles = p->kind == KIND_LITERAL ? 0 : (size_t)(g->mode == SRB_MODE_FAR ? 6 : 3) * ((t->totalSteps_host + 1) & ~(uint64_t)1);
   if (!unlimited) {
     if (scratch_bytes >= p->preDoubles * 8) scratch_bytes -= p->preDoubles * 8;
     else p->preDoubles = 0;
   }
+  // fp64 pair kernel on the tensor cores: warp-specialised form (srb_ws.cuh) whenever the pre-pass planes exist
+  // (SRB_WS=0 keeps the round-1 warp-autonomous form: A/B measurements)
+  p->ws = false;
+  {
+    const char* e = std::getenv("SRB_WS");
+    if (p->kind == KIND_PAIR && g->dtype == SRB_DTYPE_F64 && (p->tw * p->nc) % 8 == 0 && p->preDoubles > 0 &&
+        !(e && std::atoi(e) == 0))
+      p->ws = pick_ws(p->tw, p->nc, &p->L);
+  }
+  if (p->ws) {             // packed 9-double records (x, y, z, a, b) instead of 6 planes
+    const size_t packed = 9 * (size_t)t->totalSteps_host + 2;
+    if (unlimited || scratch_bytes + p->preDoubles * 8 >= packed * 8) {
+      if (!unlimited) scratch_bytes = scratch_bytes + p->preDoubles * 8 - packed * 8;
+      p->preDoubles = packed;
+    } else {               // scratch too small for the records: the warp-autonomous form with the planes
+      p->ws = false;
+      pick(p->kind, g->mode, g->dtype, p->native, p->tw, p->nc, &p->L);
+    }
+  }
+  p->chunkNodes = (uint32_t)p->L.chunk;
+  p->nChunks = (g->nOmega + p->chunkNodes - 1) / p->chunkNodes;
+  p->nVD = g->nPhi * g->nAxis2 * p->nChunks;
+  p->nVDtiles = (p->nVD + p->L.units - 1) / p->L.units;
+  p->nOut = srb_num_spectra(g->mode, g->comp);
+  p->perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
+  p->slabDoubles = p->perOut * p->nOut;
+  SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->L.smem));
+  SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, p->L.threads, p->L.smem));
+  if (p->blocksPerSM < 1) return fail("kernel does not fit on an SM");
+  // particle chunks: fill whole waves of the machine; bounded by tracks, scratch and 64 waves
+  const uint64_t slots = (uint64_t)p->numSM * p->blocksPerSM;
+  uint64_t maxPC = t->nTracks ? t->nTracks : 1;
   const uint64_t slabCap = unlimited ? (uint64_t)(1ull << 30) / (p->slabDoubles * 8) : scratch_bytes / (p->slabDoubles * 8);
   maxPC = std::min<uint64_t>(maxPC, 1 + slabCap);
   maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, (64 * slots) / p->nVDtiles));
@@ -441,20 +712,23 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   P.snapStride = t->itSnapsStride;
   for (int c = 0; c < p.nOut; c++) P.out[c] = spectra[c];
   double* preBuf = p.preDoubles ? (double*)scratch : nullptr;
-  P.pre = preBuf; P.preStride = t->totalSteps_host;
+  P.pre = preBuf; P.preStride = (t->totalSteps_host + 1) & ~(uint64_t)1;
+  // TMA bulk copies need 16-byte aligned sources: the arrays themselves must be (torch allocations are)
+  P.tmaOK = (((uintptr_t)preBuf & 15u) == 0) ? 1 : 0;
+  P.prePacked = p.ws ? 1 : 0;
   P.slabs = (double*)scratch + p.preDoubles; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
   P.counters = (unsigned long long*)counters;
   uint32_t launched = 0;
   if (preBuf) {
     const uint64_t total = t->totalSteps_host;
     const int pb = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)p.numSM * 16);
-    k_prepass<<<pb, 256, 0, stream>>>(P, preBuf, total);
+    k_prepass<<<pb, 256, 0, stream>>>(P, preBuf, total, P.preStride);
     SRB_CUDA(cudaGetLastError());
     launched++;
   }
   if (p.nPC > 1) SRB_CUDA(cudaMemsetAsync(P.slabs, 0, (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double), stream));
   const uint32_t blocks = p.nVDtiles * p.nPC;
-  p.L.kernel<<<blocks, NW * 32, p.L.smem, stream>>>(P);
+  p.L.kernel<<<blocks, p.L.threads, p.L.smem, stream>>>(P);
   SRB_CUDA(cudaGetLastError());
   launched++;
   if (p.nPC > 1) {
@@ -466,7 +740,7 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   }
   g_info.kind = p.kind; g_info.tile_width = p.tw; g_info.chunk_nodes = p.chunkNodes; g_info.n_chunks = p.nChunks;
   g_info.n_virtual_dirs = p.nVD; g_info.n_particle_chunks = p.nPC; g_info.grid_blocks = blocks;
-  g_info.block_threads = NW * 32; g_info.n_components = (uint32_t)p.nc; g_info.smem_bytes = (uint32_t)p.L.smem; g_info.kernels_launched = launched;
+  g_info.block_threads = (uint32_t)p.L.threads; g_info.n_components = (uint32_t)p.nc; g_info.smem_bytes = (uint32_t)p.L.smem; g_info.kernels_launched = launched;
   return 0;
 }
 

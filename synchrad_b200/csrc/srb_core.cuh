@@ -249,6 +249,8 @@ struct Params {
   // near: beta0,beta1,beta2.  nullptr -> the prep phase computes them itself.
   const double* pre;
   uint64_t preStride;
+  int32_t tmaOK;        // pre is 16-byte aligned (TMA staging of srb_ws.cuh)
+  int32_t prePacked;    // pre holds one 9-double record per step: x, y, z, a0..a2, b0..b2 (warp-specialised kernel)
 };
 
 // NC: amplitude components carried per node in far-field mode.
@@ -368,15 +370,10 @@ template <class TI> SRB_HD double ldv(const void* p, size_t i) { return (double)
 // Everything below is per (direction, step) and follows the oracle's operation order exactly
 // (no contraction), so that for TI=double tau and the amplitude vector are bit-identical to the
 // strict restatement of kernel_farfield.cl:65-94 / kernel_nearfield.cl:64-85.
+// Lienard-Wiechert amplitude vector of one far-field step from the step's acceleration a and mean beta b
+// (kernel_farfield.cl:84-94), in the basis the configuration carries (see Cfg::NC)
 template <class C>
-SRB_HD void prep_far(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
-                     double dtInv, double A[3]) {
-  using TI = typename C::TI;
-  double a[3], b[3];
-  if (tv.pre) {
-#pragma unroll
-    for (int c = 0; c < 3; c++) { a[c] = tv.pre[c * P.preStride + it]; b[c] = tv.pre[(3 + c) * P.preStride + it]; }
-  } else far_step_kinematics<TI>(tv.ux, tv.uy, tv.uz, it, dtInv, a, b);
+SRB_HD void far_amplitude(const Params& P, const Geom& g, const double a[3], const double b[3], double A[3]) {
   double c1 = sdot3(a[0], a[1], a[2], g.nx, g.ny, g.nz);
   double c2 = ssub(1.0, sdot3(b[0], b[1], b[2], g.nx, g.ny, g.nz));
   c2 = sdiv(1.0, c2);
@@ -393,6 +390,18 @@ SRB_HD void prep_far(const Params& P, const Geom& g, const TrackView& tv, uint32
     A[1] = sdot3(g.tx, g.ty, g.tz, A0, A1, A2);
     A[2] = sdot3(g.px, g.py, g.pz, A0, A1, A2);
   } else { A[0] = A0; A[1] = A1; A[2] = A2; }
+}
+
+template <class C>
+SRB_HD void prep_far(const Params& P, const Geom& g, const TrackView& tv, uint32_t it,
+                     double dtInv, double A[3]) {
+  using TI = typename C::TI;
+  double a[3], b[3];
+  if (tv.pre) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { a[c] = tv.pre[c * P.preStride + it]; b[c] = tv.pre[(3 + c) * P.preStride + it]; }
+  } else far_step_kinematics<TI>(tv.ux, tv.uy, tv.uz, it, dtInv, a, b);
+  far_amplitude<C>(P, g, a, b, A);
 }
 
 // tau of step it-1 (the reference's phasePrev/omega), or 0 for it == 0 (Q1)
@@ -813,47 +822,68 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
   }
 }
 
+// geometry of virtual direction vd: node range of the omega chunk, unit vector n (far) / screen point (near), e_theta, e_phi
+template <class C>
+SRB_HD void make_geom(const Params& P, uint32_t vd, Geom& g) {
+  using TI = typename C::TI;
+  const uint32_t ch = vd % P.nChunks; const uint32_t d = vd / P.nChunks;
+  g.iA2 = d % P.nA2; g.iPhi = d / P.nA2;
+  g.cLo = ch * P.chunkNodes; g.cHi = g.cLo + P.chunkNodes < P.nOmega ? g.cLo + P.chunkNodes : P.nOmega;
+  const double sP = ldv<TI>(P.sinPhi, g.iPhi), cP = ldv<TI>(P.cosPhi, g.iPhi);
+  if (C::MODE == MODE_FAR) {
+    const double sT = ldv<TI>(P.axA, g.iA2), cT = ldv<TI>(P.axB, g.iA2);
+    if (C::KIND != KIND_LITERAL) { g.nx = smul(sT, cP); g.ny = smul(sT, sP); g.nz = cT; g.tx = smul(cT, cP); g.ty = smul(cT, sP); }
+    else {  // the reference forms n in fp32 (kernel_farfield.cl:40-42)
+      g.nx = (double)((float)sT * (float)cP); g.ny = (double)((float)sT * (float)sP); g.nz = cT;
+      g.tx = (double)((float)cT * (float)cP); g.ty = (double)((float)cT * (float)sP);
+    }
+    g.tz = -sT; g.px = -sP; g.py = cP; g.pz = 0.0;
+  } else {
+    const double r = ldv<TI>(P.axA, g.iA2);
+    if (C::KIND != KIND_LITERAL) { g.nx = smul(r, cP); g.ny = smul(r, sP); }
+    else { g.nx = (double)((float)r * (float)cP); g.ny = (double)((float)r * (float)sP); }
+    g.nz = P.L;
+    g.tx = g.ty = g.tz = g.px = g.py = g.pz = 0.0;
+  }
+}
+
+// particle chunk -> track range [t0, t1), balanced by cumulative steps (offsets is a prefix sum)
+SRB_HD void chunk_tracks(const Params& P, uint32_t pc, uint32_t& t0, uint32_t& t1) {
+  const uint64_t total = P.offsets[P.nTracks];
+  auto bound = [&](uint32_t c) -> uint32_t {
+    if (c == 0) return 0u;
+    if (c >= P.nPC) return P.nTracks;
+    const uint64_t target = (total / P.nPC) * c + ((total % P.nPC) * c) / P.nPC;
+    uint32_t a = 0, b = P.nTracks;      // first track whose start offset >= target
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (P.offsets[mid] < target) a = mid + 1; else b = mid; }
+    return a;
+  };
+  t0 = bound(pc); t1 = bound(pc + 1);
+}
+
+// track t of the batch
+template <class C>
+SRB_HD void load_track(const Params& P, uint32_t t, TrackView& tv) {
+  using TI = typename C::TI;
+  const uint64_t o = P.offsets[t];
+  tv.n = (uint32_t)(P.offsets[t + 1] - o);
+  tv.x = (const TI*)P.x + o; tv.y = (const TI*)P.y + o; tv.z = (const TI*)P.z + o;
+  tv.ux = (const TI*)P.ux + o; tv.uy = (const TI*)P.uy + o; tv.uz = (const TI*)P.uz + o;
+  tv.pre = P.pre ? P.pre + o : nullptr;
+  tv.itStart = P.itStart[t]; tv.itEnd = P.itEnd[t];
+  tv.snaps = P.itSnaps + (size_t)P.snapStride * t;
+  tv.w = ldv<TI>(P.w, t);
+}
+
 // -------------------------------------------------------------------------------- warp task
 // One warp integrates all tracks of particle chunk `pc` for virtual direction `vd`.
 template <class C>
 SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm, ThreadState<C>* st) {
   using TI = typename C::TI; using TM = typename C::TM;
   Geom g;
-  {
-    const uint32_t ch = vd % P.nChunks; const uint32_t d = vd / P.nChunks;
-    g.iA2 = d % P.nA2; g.iPhi = d / P.nA2;
-    g.cLo = ch * P.chunkNodes; g.cHi = g.cLo + P.chunkNodes < P.nOmega ? g.cLo + P.chunkNodes : P.nOmega;
-    const double sP = ldv<TI>(P.sinPhi, g.iPhi), cP = ldv<TI>(P.cosPhi, g.iPhi);
-    if (C::MODE == MODE_FAR) {
-      const double sT = ldv<TI>(P.axA, g.iA2), cT = ldv<TI>(P.axB, g.iA2);
-      if (C::KIND != KIND_LITERAL) { g.nx = smul(sT, cP); g.ny = smul(sT, sP); g.nz = cT; g.tx = smul(cT, cP); g.ty = smul(cT, sP); }
-      else {  // the reference forms n in fp32 (kernel_farfield.cl:40-42)
-        g.nx = (double)((float)sT * (float)cP); g.ny = (double)((float)sT * (float)sP); g.nz = cT;
-        g.tx = (double)((float)cT * (float)cP); g.ty = (double)((float)cT * (float)sP);
-      }
-      g.tz = -sT; g.px = -sP; g.py = cP; g.pz = 0.0;
-    } else {
-      const double r = ldv<TI>(P.axA, g.iA2);
-      if (C::KIND != KIND_LITERAL) { g.nx = smul(r, cP); g.ny = smul(r, sP); }
-      else { g.nx = (double)((float)r * (float)cP); g.ny = (double)((float)r * (float)sP); }
-      g.nz = P.L;
-      g.tx = g.ty = g.tz = g.px = g.py = g.pz = 0.0;
-    }
-  }
-  // particle chunk -> track range, balanced by cumulative steps (offsets is a prefix sum)
+  make_geom<C>(P, vd, g);
   uint32_t t0, t1;
-  {
-    const uint64_t total = P.offsets[P.nTracks];
-    auto bound = [&](uint32_t c) -> uint32_t {
-      if (c == 0) return 0u;
-      if (c >= P.nPC) return P.nTracks;
-      const uint64_t target = (total / P.nPC) * c + ((total % P.nPC) * c) / P.nPC;
-      uint32_t a = 0, b = P.nTracks;      // first track whose start offset >= target
-      while (a < b) { const uint32_t mid = (a + b) >> 1; if (P.offsets[mid] < target) a = mid + 1; else b = mid; }
-      return a;
-    };
-    t0 = bound(pc); t1 = bound(pc + 1);
-  }
+  chunk_tracks(P, pc, t0, t1);
   const double dtInv = sdiv(1.0, P.dt);
   if constexpr (C::MMA) {
     // masked steps of the tensor-core main phase multiply stale staging data by 0: keep it finite from the start
@@ -877,14 +907,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
 
   for (uint32_t t = t0; t < t1; t++) {
     TrackView tv;
-    const uint64_t o = P.offsets[t];
-    tv.n = (uint32_t)(P.offsets[t + 1] - o);
-    tv.x = (const TI*)P.x + o; tv.y = (const TI*)P.y + o; tv.z = (const TI*)P.z + o;
-    tv.ux = (const TI*)P.ux + o; tv.uy = (const TI*)P.uy + o; tv.uz = (const TI*)P.uz + o;
-    tv.pre = P.pre ? P.pre + o : nullptr;
-    tv.itStart = P.itStart[t]; tv.itEnd = P.itEnd[t];
-    tv.snaps = P.itSnaps + (size_t)P.snapStride * t;
-    tv.w = ldv<TI>(P.w, t);
+    load_track<C>(P, t, tv);
     SRB_LANES_BEGIN
 #pragma unroll
       for (int k = 0; k < C::NACC; k++) SRB_ST.acc[k] = (TM)0;

@@ -9,6 +9,7 @@
 
 #include "../../include/synchrad_b200.h"
 #include "../../synchrad_b200/csrc/srb_literal.cuh"
+#include "../../synchrad_b200/csrc/srb_ws.cuh"
 
 using namespace srb;
 
@@ -25,6 +26,21 @@ static void run_all(const Params& P0, unsigned long long* counters) {
     ThreadState<C> st[32];
     std::memset(&sm, 0, sizeof sm);
     warp_task<C>(P, vd, pc, sm, st);
+    tot[0] += cnt[0]; tot[1] += cnt[1];
+  }
+  if (counters) { counters[0] = tot[0]; counters[1] = tot[1]; }
+}
+
+// warp-specialised pair kernel (srb_ws.cuh): producer and consumer of a unit run in sequence per item
+template <class C>
+static void run_all_ws(const Params& P0, unsigned long long* counters) {
+  unsigned long long tot[2] = {0, 0};
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : tot[:2])
+  for (long long task = 0; task < (long long)P0.nVD * P0.nPC; task++) {
+    Params P = P0;
+    unsigned long long cnt[2] = {0, 0};
+    P.counters = cnt;
+    ws_emulate_task<C>(P, (uint32_t)(task % P0.nVD), (uint32_t)(task / P0.nVD));
     tot[0] += cnt[0]; tot[1] += cnt[1];
   }
   if (counters) { counters[0] = tot[0]; counters[1] = tot[1]; }
@@ -49,6 +65,7 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   P.descending = g->omega_last_host < g->omega_first_host ? 1 : 0;
   P.domega = g->nOmega > 1 ? (g->omega_last_host - g->omega_first_host) / (double)(g->nOmega - 1) : 0.0;
   if (g->dtype == SRB_DTYPE_F32_LITERAL) kind = KIND_LITERAL;
+  const bool ws = kind == 6;          // 'pair_ws': the warp-specialised form of the fp64 pair kernel (needs the pre-pass)
   const int tiles = kind == KIND_RECUR ? 16 : 32;
   P.chunkNodes = (uint32_t)(tiles * tw);
   P.nChunks = (g->nOmega + P.chunkNodes - 1) / P.chunkNodes;
@@ -116,6 +133,15 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
 #define EMU_LIT(M, TWV) if (kind == KIND_LITERAL && g->mode == M && tw == TWV) { run_all<Cfg<double, float, M, KIND_LITERAL, TWV, false, 3>>(P, counters); ok = true; }
   EMU_LIT(MODE_FAR, 8) EMU_LIT(MODE_FAR, 4) EMU_LIT(MODE_FAR, 2) EMU_LIT(MODE_NEAR, 8) EMU_LIT(MODE_NEAR, 4) EMU_LIT(MODE_NEAR, 2)
 #undef EMU_LIT
+  if (ws) {
+    ok = false;
+    if (g->mode == MODE_FAR && !f32 && P.pre) {
+      if (tw == 8 && !spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 2>>(P, counters); ok = true; }
+      if (tw == 16 && !spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 16, false, 2>>(P, counters); ok = true; }
+      if (tw == 4 && !spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 4, false, 2>>(P, counters); ok = true; }
+      if (tw == 8 && spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 3>>(P, counters); ok = true; }
+    }
+  }
   if (!ok) return -1;
   for (uint32_t s = 0; s + 1 < nPC; s++)
     for (int c = 0; c < nOut; c++)

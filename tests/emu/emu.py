@@ -14,7 +14,8 @@ _SO = os.path.join(_HERE, 'libsrb_emu.so')
 _SRC = [os.path.join(_HERE, 'emu.cpp'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_pair.cuh'),
-        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh')]
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh'),
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_ws.cuh')]
 
 
 def build(so=None, defines=()):
@@ -68,12 +69,12 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     keys = host.COMP_KEYS[comp]
     spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
     sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
-    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4}[kind]
+    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4, 'pair_ws': 6}[kind]
     if literal:
         kind_i, tw = 0, None   # the C side switches to the literal kind; tile widths of the direct layout
     if tw is None:
         tiles = 16 if kind_i == 1 else 32
-        opts = ([4, 8, 16] if A['mode'] == 'far' else [2, 4, 8]) if kind_i == 1 else ([4, 8] if kind_i == 4 else ([2, 4, 8, 16] if kind_i == 3 and not comp.startswith('spheric') else [2, 4, 8]))   # as make_plan (srb_api.cu)
+        opts = ([4, 8, 16] if A['mode'] == 'far' else [2, 4, 8]) if kind_i == 1 else ([4, 8] if kind_i == 4 else ([2, 4, 8, 16] if kind_i == 3 and not comp.startswith('spheric') else ([4, 8, 16] if kind_i == 6 and not comp.startswith('spheric') else ([8] if kind_i == 6 else [2, 4, 8]))))   # as make_plan (srb_api.cu)
         tw = next((o for o in opts if tiles * o >= n_w), opts[-1])
     cnt = (ctypes.c_ulonglong * 2)(0, 0)
     lib.srb_emu_integrate.restype = ctypes.c_int
