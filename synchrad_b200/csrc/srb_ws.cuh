@@ -34,8 +34,9 @@
 
 namespace srb {
 
-constexpr int WS_XS = 34;   // doubles per X row: lane = step stores and A-fragment loads are both bank-conflict free
-constexpr int WS_QS = 36;   // doubles per Q' row: same for the B fragments
+constexpr int WS_XS = 36;   // (Re, Im) pairs per row of the stage arrays: lane = step 128-bit stores and the fragment
+                            // loads of the consumer (128-bit X / W, 64-bit halves of Q') are all bank-conflict free
+struct alignas(16) Dbl2 { double x, y; };
 constexpr int WS_IN = 34;   // staged input records per sub-batch (32 steps + the previous step + 16-byte alignment slack)
 constexpr int WS_NIN = 9;   // doubles per input record: x, y, z, a0..a2, b0..b2 (written by the pre-pass kernel)
 
@@ -54,14 +55,14 @@ SRB_HD void ws_const(const Params& P, const Geom& g, WsConst& k) {
 
 template <class C>
 struct alignas(16) WsStage {
-  double X[16][WS_XS];              // [2*tile + (Re|Im)][step], tiles 0..7; tiles 8.. = X_b * R^8 / R^16 / R^24 (consumer)
-  double W[4][WS_QS];               // R^8 (rows 0, 1) and R^16 (rows 2, 3): (Re|Im)[step]
-  double Q[8 * C::NT][WS_QS];       // [2*(pair*NC + comp) + (cos|sin)][step]
-  double rec[SUB][4];               // A[NC] and tau (index 3) of the step, for the lane-by-lane path
+  Dbl2 X[8][WS_XS];                 // [tile][step] = (Re, Im) X, tiles 0..7; tiles 8.. = X_b * R^8 / R^16 / R^24 (consumer)
+  Dbl2 W[2][WS_XS];                 // R^8 and R^16: [power][step]
+  Dbl2 Q[4 * C::NT][WS_XS];         // [pair*NC + comp][step] = A_comp * (cos, sin) of the pair offset
+  Dbl2 rec[SUB][2];                 // (A0, A1), (A2, tau) of the step, for the lane-by-lane path
   uint32_t rng[SUB];                // lo | hi<<10 | flag<<30 (chunk-relative pass range)
   uint32_t cnt, fullMask, anyMask, pad;
   // a flush item hands the stage to the consumer as scratch for 32 * NACC doubles (16-node tiles need a little more)
-  static constexpr int BASE_DOUBLES = 16 * WS_XS + 4 * WS_QS + 8 * C::NT * WS_QS + SUB * 4 + SUB / 2 + 2;
+  static constexpr int BASE_DOUBLES = 2 * (8 + 2 + 4 * C::NT) * WS_XS + SUB * 4 + SUB / 2 + 2;
   static constexpr int PAD_DOUBLES = 32 * C::NACC > BASE_DOUBLES ? 32 * C::NACC - BASE_DOUBLES : 2;
   double flushPad[PAD_DOUBLES];
 };
@@ -139,26 +140,49 @@ SRB_HD void ws_seeds(const Params& P, const WsConst& kc, double tau, const doubl
   {
     double x0r = er, x0i = ei;
     double x1r = er * cd - ei * sd, x1i = er * sd + ei * cd;
-    sg.X[0][s] = x0r; sg.X[1][s] = x0i; sg.X[2][s] = x1r; sg.X[3][s] = x1i;
+    sg.X[0][s] = Dbl2{x0r, x0i}; sg.X[1][s] = Dbl2{x1r, x1i};
 #pragma unroll
     for (int k = 2; k < 8; k++) {
       const double x2r = fma(cf, x1r, -x0r), x2i = fma(cf, x1i, -x0i);
-      sg.X[2 * k][s] = x2r; sg.X[2 * k + 1][s] = x2i;
+      sg.X[k][s] = Dbl2{x2r, x2i};
       x0r = x1r; x0i = x1i; x1r = x2r; x1i = x2i;
     }
   }
   double qr = r8r * r8r - r8i * r8i, qi = 2.0 * r8r * r8i;           // R^16
-  sg.W[0][s] = r8r; sg.W[1][s] = r8i; sg.W[2][s] = qr; sg.W[3][s] = qi;
+  sg.W[0][s] = Dbl2{r8r, r8i}; sg.W[1][s] = Dbl2{qr, qi};
   const double wr = qr * qr - qi * qi, wi = 2.0 * qr * qi;           // R^32
 #pragma unroll
   for (int p = 0; p < TW / 2; p++) {
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      sg.Q[2 * (p * NC + c)][s] = A[c] * qr;
-      sg.Q[2 * (p * NC + c) + 1][s] = A[c] * qi;
+      sg.Q[p * NC + c][s] = Dbl2{A[c] * qr, A[c] * qi};
     }
     if (p + 1 < TW / 2) { const double t = qr * wr - qi * wi; qi = qr * wi + qi * wr; qr = t; }
   }
+}
+
+// Amplitude in the transverse basis with fewer FP64 ops than far_amplitude (47 -> 33): the denominator 1 - b.n, where
+// the cancellation is (relative error ~ gamma^2 ulp, it has to match the reference's rounding), stays in the
+// reference's operation order; its reciprocal by MUFU + two Newton steps (<= 1 ulp from the correctly rounded
+// quotient, a RELATIVE error of 1e-16 on the amplitude) and the two projections with fused multiply-adds.
+SRB_HD void far_amplitude_tr(const Geom& g, const double a[3], const double b[3], double A[3]) {
+  double c1 = sdot3(a[0], a[1], a[2], g.nx, g.ny, g.nz);
+  const double d = ssub(1.0, sdot3(b[0], b[1], b[2], g.nx, g.ny, g.nz));
+#if defined(__CUDA_ARCH__)
+  double c2;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(c2) : "d"(d));
+  c2 = fma(fma(-d, c2, 1.0), c2, c2);
+  c2 = fma(fma(-d, c2, 1.0), c2, c2);
+#else
+  const double c2 = 1.0 / d;
+#endif
+  c1 = smul(smul(c1, c2), c2);
+  const double A0 = ssub(smul(c1, ssub(g.nx, b[0])), smul(c2, a[0]));
+  const double A1 = ssub(smul(c1, ssub(g.ny, b[1])), smul(c2, a[1]));
+  const double A2 = ssub(smul(c1, ssub(g.nz, b[2])), smul(c2, a[2]));
+  A[0] = fma(g.tx, A0, fma(g.ty, A1, g.tz * A2));
+  A[1] = fma(g.px, A0, g.py * A1);          // e_phi = (-sin phi, cos phi, 0)
+  A[2] = 0.0;
 }
 
 // One step of the producer's sub-batch (lane = step), in two parts.  tau / tauPrev come from the caller (it owns the
@@ -182,7 +206,7 @@ SRB_HD void ws_prep_guard(const Params& P, const Geom& g, const WsConst& kc, boo
     }
     nAll += n;
     if (w.flag) {
-      far_amplitude<C>(P, g, a, b, w.A);
+      if (C::NC == 2) far_amplitude_tr(g, a, b, w.A); else far_amplitude<C>(P, g, a, b, w.A);
       // beyond |phase| = 2^18 the seed arithmetic cannot track the reference's rounded phase to 1e-9: node by node
       if (fabs(kc.wHi * tau) > 262144.0) w.flag = 3u;
       nPass += w.hi - w.lo;
@@ -194,7 +218,7 @@ template <class C>
 SRB_HD uint32_t ws_prep_store(const Params& P, const WsConst& kc, const WsStep& w, WsStage<C>& sg, int lane) {
   if (w.flag) {
     if (w.flag != 3u) ws_seeds<C>(P, kc, w.tau, w.A, sg, lane);
-    sg.rec[lane][0] = w.A[0]; sg.rec[lane][1] = w.A[1]; sg.rec[lane][2] = w.A[2]; sg.rec[lane][3] = w.tau;
+    sg.rec[lane][0] = Dbl2{w.A[0], w.A[1]}; sg.rec[lane][1] = Dbl2{w.A[2], w.tau};
   }
   sg.rng[lane] = w.lo | (w.hi << 10) | (w.flag << 30);
   return w.flag;
@@ -213,15 +237,15 @@ SRB_HD void ws_partial(const Params& P, const Geom& g, const WsStage<C>& sg, uin
     const uint32_t r = sg.rng[s];
     const uint32_t flag = r >> 30;
     const int hiN = (int)((r >> 10) & 0x3ffu);          // passing chunk-relative nodes: [0, hiN)
-    const double tau = sg.rec[s][3];                    // flag 3 only
+    const double tau = sg.rec[s][1].y;                  // flag 3 only
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       const int m = 8 * a + b;
       double xr = 0, xi = 0;
       if (flag != 3) {
-        xr = sg.X[2 * b][s]; xi = sg.X[2 * b + 1][s];
-        if (a & 1) { const double wr = sg.W[0][s], wi = sg.W[1][s]; const double t = fma(xr, wr, -(xi * wi)); xi = fma(xr, wi, xi * wr); xr = t; }
-        if (a & 2) { const double wr = sg.W[2][s], wi = sg.W[3][s]; const double t = fma(xr, wr, -(xi * wi)); xi = fma(xr, wi, xi * wr); xr = t; }
+        xr = sg.X[b][s].x; xi = sg.X[b][s].y;
+        if (a & 1) { const double wr = sg.W[0][s].x, wi = sg.W[0][s].y; const double t = fma(xr, wr, -(xi * wi)); xi = fma(xr, wi, xi * wr); xr = t; }
+        if (a & 2) { const double wr = sg.W[1][s].x, wi = sg.W[1][s].y; const double t = fma(xr, wr, -(xi * wi)); xi = fma(xr, wi, xi * wr); xr = t; }
       }
 #pragma unroll
       for (int t = 0; t < NT; t++) {
@@ -231,13 +255,13 @@ SRB_HD void ws_partial(const Params& P, const Geom& g, const WsStage<C>& sg, uin
         const bool pp = m + 32 * kp < hiN;
         double cp = 0, sp = 0, cm, sm_;
         if (flag == 3) {
-          const double A = sg.rec[s][c];
+          const double A = c == 0 ? sg.rec[s][0].x : (c == 1 ? sg.rec[s][0].y : sg.rec[s][1].x);
           const uint32_t jb = g.cLo + (uint32_t)m;
           sincos_big(smul((double)((const TI*)P.omega)[jb + 32 * km], tau), &sm_, &cm);
           if (pp) sincos_big(smul((double)((const TI*)P.omega)[jb + 32 * kp], tau), &sp, &cp);
           cp *= A; sp *= A; cm *= A; sm_ *= A;
         } else {
-          const double qc = sg.Q[2 * q][s], qs = sg.Q[2 * q + 1][s];
+          const double qc = sg.Q[q][s].x, qs = sg.Q[q][s].y;
           if (pp) { cp = fma(xr, qc, -(xi * qs)); sp = fma(xr, qs, xi * qc); }   // X * A Q
           cm = fma(xr, qc, xi * qs); sm_ = fma(xi, qc, -(xr * qs));              // X * A conj(Q)
         }
@@ -260,9 +284,13 @@ SRB_HD void ws_load_frag_k(const WsStage<C>& sg, int j, int ks, int b, uint32_t 
   const int s = 4 * j + ks;
   const bool on = (fullMask >> s) & 1u;
 #pragma unroll
-  for (int t = 0; t < C::NT; t++) { const double v = sg.Q[8 * t + b][s]; f.bq[t] = on ? v : 0.0; }
-  f.xr = sg.X[2 * b][s]; f.xi = sg.X[2 * b + 1][s];
-  f.ur = sg.W[0][s]; f.ui = sg.W[1][s]; f.wr = sg.W[2][s]; f.wi = sg.W[3][s];
+  for (int t = 0; t < C::NT; t++) {       // column 8t + b of Q' = (cos|sin)[b & 1] of q = 4t + b/2
+    const Dbl2& qq = sg.Q[4 * t + (b >> 1)][s];
+    const double v = (b & 1) ? qq.y : qq.x;
+    f.bq[t] = on ? v : 0.0;
+  }
+  const Dbl2 xx = sg.X[b][s], uu = sg.W[0][s], ww = sg.W[1][s];
+  f.xr = xx.x; f.xi = xx.y; f.ur = uu.x; f.ui = uu.y; f.wr = ww.x; f.wi = ww.y;
 }
 template <class C>
 SRB_HD void ws_mma_k(const WsFrag<C>& f, ThreadState<C>& st) {
@@ -320,9 +348,9 @@ inline void ws_main(const Params& P, const Geom& g, const WsStage<C>& sg, Thread
     for (int lane = 0; lane < 32; lane++) {
       const int ks = lane & 3, b = lane >> 2, s = 4 * j + ks;
       const bool on = (fullMask >> s) & 1u;
-      for (int t = 0; t < NT; t++) bq[t][lane] = on ? sg.Q[8 * t + b][s] : 0.0;
-      xr[0][lane] = sg.X[2 * b][s]; xi[0][lane] = sg.X[2 * b + 1][s];
-      const double ur = sg.W[0][s], ui = sg.W[1][s], wr = sg.W[2][s], wi = sg.W[3][s];
+      for (int t = 0; t < NT; t++) bq[t][lane] = on ? ((b & 1) ? sg.Q[4 * t + (b >> 1)][s].y : sg.Q[4 * t + (b >> 1)][s].x) : 0.0;
+      xr[0][lane] = sg.X[b][s].x; xi[0][lane] = sg.X[b][s].y;
+      const double ur = sg.W[0][s].x, ui = sg.W[0][s].y, wr = sg.W[1][s].x, wi = sg.W[1][s].y;
       xr[1][lane] = fma(xr[0][lane], ur, -(xi[0][lane] * ui)); xi[1][lane] = fma(xr[0][lane], ui, xi[0][lane] * ur);
       for (int a = 2; a < 4; a++) {
         xr[a][lane] = fma(xr[a - 2][lane], wr, -(xi[a - 2][lane] * wi));
