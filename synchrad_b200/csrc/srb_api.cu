@@ -109,12 +109,15 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
   WsSmem<C, NU, NP, NS>& S = *reinterpret_cast<WsSmem<C, NU, NP, NS>*>(smraw);
   static_assert(sizeof(WsStage<C>) >= 32 * C::NACC * sizeof(double), "stage too small for the flush transposes");
   static_assert(sizeof(WsStage<C>) % 16 == 0, "stages keep the input rows 16-byte aligned");
+  // a producer must observe every phase of the empty barriers it waits on (parity waits): with stage = k % NS and
+  // producer = k % NP that holds iff each stage is always served by the same producer
+  static_assert(NS % NP == 0, "ring stages must map to a fixed producer");
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
   // masked steps of the tensor-core stream multiply stale stage data by 0: keep it finite from the start
   for (uint32_t k = threadIdx.x; k < sizeof(S.stage) / 4u; k += blockDim.x) reinterpret_cast<uint32_t*>(&S.stage)[k] = 0u;
   if (threadIdx.x == 0) {
     for (int u = 0; u < NU; u++) {
-      for (int i = 0; i < NS; i++) { mbar_init(&S.full[u][i], 32); mbar_init(&S.empty[u][i], 32); mbar_init(&S.xfer[u][i], 32); }
+      for (int i = 0; i < NS; i++) { mbar_init(&S.full[u][i], 32); mbar_init(&S.empty[u][i], 32 * NCW); mbar_init(&S.xfer[u][i], 32); }
       for (int q = 0; q < NP; q++) mbar_init(&S.inbar[u][q], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -149,14 +152,16 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
         for (int q = 0; q < C::NACC; q++) st.acc[q] = 0.0;
       }
       WsStage<C>& sg = S.stage[u][sgi];
+      // EVERY consumer warp passes EVERY item's full barrier and arrives on its empty barrier (count 32 * NCW), whether
+      // it processes the item or not: a parity wait is only meaningful for a waiter that observes each phase, and a
+      // stage must not be refilled before both warps are past it -- otherwise the even and the odd items form two
+      // independent pipelines (stage = k % NS, warp = k % NCW) that drift apart and a late warp mistakes an earlier or
+      // later phase of the same parity for its own (seen as whole directions going wrong in some runs).
+      mbar_wait(&S.full[u][sgi], par);
       if (it.kind == 0) {
-        if ((int)(k % (uint32_t)NCW) == cidx) {
-          mbar_wait(&S.full[u][sgi], par);
-          ws_main<C>(P, g, sg, lane, st);
-          mbar_arrive(&S.empty[u][sgi]);
-        }
+        if ((int)(k % (uint32_t)NCW) == cidx) ws_main<C>(P, g, sg, lane, st);
+        mbar_arrive(&S.empty[u][sgi]);
       } else {
-        mbar_wait(&S.full[u][sgi], par);
         double* buf = reinterpret_cast<double*>(&sg);
         if (NCW > 1 && cidx == 1) {
           // hand this warp's sums to warp 0 (same fragment layout, lane-major) and restart from zero: warp 0 carries
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
 #pragma unroll
           for (int q = 0; q < C::NACC; q++) { buf[q * 32 + lane] = st.acc[q]; st.acc[q] = 0.0; }
           mbar_arrive(&S.xfer[u][sgi]);
+          mbar_arrive(&S.empty[u][sgi]);
         } else {
           if (NCW > 1) {
             mbar_wait(&S.xfer[u][sgi], (xph >> sgi) & 1u);
@@ -468,8 +474,8 @@ bool pick_ws(int tw, int nc, Launcher* L) {
   using srb::Cfg; using srb::KIND_PAIR; using srb::MODE_FAR;
   if (tw == 8 && nc == 2) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 2>, 4, SRB_WS_NP, SRB_WS_NS, SRB_WS_NCW>(); return true; }
   if (tw == 4 && nc == 2) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 4, false, 2>, 4, SRB_WS_NP, SRB_WS_NS, SRB_WS_NCW>(); return true; }
-  if (tw == 16 && nc == 2) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 16, false, 2>, 4, 2, 3, 1>(); return true; }
-  if (tw == 8 && nc == 3) { *L = make_launcher_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 3>, 4, SRB_WS_NP, 3, 1>(); return true; }
+  // 16-node tiles (grids with more than 256 omega nodes) and the three-component spheric kernels keep the
+  // warp-autonomous form of srb_pair.cuh: their stages (16 KB) do not leave room for a four-deep ring
   return false;
 }
 
@@ -714,7 +720,7 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   double* preBuf = p.preDoubles ? (double*)scratch : nullptr;
   P.pre = preBuf; P.preStride = (t->totalSteps_host + 1) & ~(uint64_t)1;
   // TMA bulk copies need 16-byte aligned sources: the arrays themselves must be (torch allocations are)
-  P.tmaOK = (((uintptr_t)preBuf & 15u) == 0) ? 1 : 0;
+  P.tmaOK = (((uintptr_t)preBuf & 15u) == 0 && !std::getenv("SRB_WS_NOTMA")) ? 1 : 0;      // (env: debugging aid)
   P.prePacked = p.ws ? 1 : 0;
   P.slabs = (double*)scratch + p.preDoubles; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
   P.counters = (unsigned long long*)counters;

@@ -137,9 +137,9 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
     ok = false;
     if (g->mode == MODE_FAR && !f32 && P.pre) {
       if (tw == 8 && !spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 2>>(P, counters); ok = true; }
-      if (tw == 16 && !spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 16, false, 2>>(P, counters); ok = true; }
+
       if (tw == 4 && !spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 4, false, 2>>(P, counters); ok = true; }
-      if (tw == 8 && spheric) { run_all_ws<Cfg<double, double, MODE_FAR, KIND_PAIR, 8, false, 3>>(P, counters); ok = true; }
+
     }
   }
   if (!ok) return -1;

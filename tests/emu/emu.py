@@ -74,7 +74,7 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
         kind_i, tw = 0, None   # the C side switches to the literal kind; tile widths of the direct layout
     if tw is None:
         tiles = 16 if kind_i == 1 else 32
-        opts = ([4, 8, 16] if A['mode'] == 'far' else [2, 4, 8]) if kind_i == 1 else ([4, 8] if kind_i == 4 else ([2, 4, 8, 16] if kind_i == 3 and not comp.startswith('spheric') else ([4, 8, 16] if kind_i == 6 and not comp.startswith('spheric') else ([8] if kind_i == 6 else [2, 4, 8]))))   # as make_plan (srb_api.cu)
+        opts = ([4, 8, 16] if A['mode'] == 'far' else [2, 4, 8]) if kind_i == 1 else ([4, 8] if kind_i == 4 else ([2, 4, 8, 16] if kind_i == 3 and not comp.startswith('spheric') else ([4, 8] if kind_i == 6 else [2, 4, 8])))   # as make_plan (srb_api.cu)
         tw = next((o for o in opts if tiles * o >= n_w), opts[-1])
     cnt = (ctypes.c_ulonglong * 2)(0, 0)
     lib.srb_emu_integrate.restype = ctypes.c_int

@@ -19,6 +19,8 @@ def test_random_problems_match_oracle(oracle, seed):
         kinds = ['direct'] if A.get('Features') or A['grid'][-1][0] < 2 else ['direct', 'recur']
         if 'recur' in kinds and A.get('mode', 'far') == 'far':
             kinds.append('pair')
+            if not kw['comp'].startswith('spheric'):
+                kinds.append('pair_ws')     # warp-specialised form (transverse basis, 4- and 8-node tiles)
         for kind in kinds:
             for nPC in (1, 3):
                 with contextlib.redirect_stdout(io.StringIO()):

@@ -164,3 +164,37 @@ def test_literal_fp32_mode_matches_the_fp32_oracle(oracle, near):
         assert cnt[0] == lit['passed'], (comp, cnt, lit['passed'])
         for k in rad:
             assert max(rel_errors(rad[k], lit['radiation'][k])) < 1e-6, (comp, k)
+
+
+@pytest.mark.parametrize('grid', [(256, 3, 2), (200, 2, 3), (33, 2, 2), (600, 2, 2)])
+def test_warp_specialised_pair_kernel_logic(oracle, grid):
+    """srb_ws.cuh (the headline kernel: DMMA consumer warps + producer warps over an mbarrier ring): the per-item functions
+    shared with the GPU kernel -- item iterator (tracks / snapshot intervals / sub-batches / flush items), producer step
+    (guard, amplitude, tile and pair phasors in the fragment layouts of the stage), consumer main phase (MMA spelled out),
+    lane-by-lane path for partial steps, fragment <-> tile transposes around the flush -- run producer-then-consumer in
+    sequence per item.  mbarriers, TMA and the role split are GPU-only (tests -m gpu)."""
+    tr, dt = cases.c5_tracks_numpy(3, 500)
+    tr = [t[:7] + [s] for t, s in zip(tr, (0, 4, 9))]
+    args = cases.c5_args(grid=grid)
+    for kw in (dict(), dict(comp='cartesian', nSnaps=3, it_range=(0, 480)), dict(comp='cartesian_complex', sigma_particle=1e-5)):
+        ref = oracle.calculate_spectrum(args, tr, dt, **kw)
+        for nPC in (1, 2):
+            rad, cnt = emu.run(args, tr, dt, kind='pair_ws', nPC=nPC, **kw)
+            for key, r in ref['radiation'].items():
+                assert max(rel_errors(rad[key], r)) < 1e-10, (grid, kw, key, rel_errors(rad[key], r))
+            if 'it_range' not in kw:
+                assert cnt[0] == ref['passed']
+    # guard-dominated input (partial steps dominate) and SI units (|phase| > 2^18: node-by-node fallback)
+    trw, dtw, infow = cases.wiggler_tracks(4, 256)
+    argw = cases.wiggler_args(infow, grid=(grid[0], 3, 2))
+    ref = oracle.calculate_spectrum(argw, trw, dtw, comp='cartesian', nSnaps=3)
+    rad, cnt = emu.run(argw, trw, dtw, kind='pair_ws', comp='cartesian', nSnaps=3)
+    for key, r in ref['radiation'].items():
+        assert max(rel_errors(rad[key], r)) < 1e-9, (key, rel_errors(rad[key], r))
+    assert cnt[0] == ref['passed']
+    trs, dts, infos = cases.wiggler_tracks(3, 256, si_scale=1e-3)
+    args_si = cases.wiggler_args(infos, grid=(grid[0], 2, 2), si_scale=1e-3)
+    ref = oracle.calculate_spectrum(args_si, trs, dts, comp='cartesian_complex')
+    rad, _ = emu.run(args_si, trs, dts, kind='pair_ws', comp='cartesian_complex')
+    for key, r in ref['radiation'].items():
+        assert max(rel_errors(rad[key], r)) < 1e-9, (key, rel_errors(rad[key], r))
