@@ -117,7 +117,7 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
   for (uint32_t k = threadIdx.x; k < sizeof(S.stage) / 4u; k += blockDim.x) reinterpret_cast<uint32_t*>(&S.stage)[k] = 0u;
   if (threadIdx.x == 0) {
     for (int u = 0; u < NU; u++) {
-      for (int i = 0; i < NS; i++) { mbar_init(&S.full[u][i], 32); mbar_init(&S.empty[u][i], 32 * NCW); mbar_init(&S.xfer[u][i], 32); }
+      for (int i = 0; i < NS; i++) { mbar_init(&S.full[u][i], 32); mbar_init(&S.empty[u][i], 32); mbar_init(&S.xfer[u][i], 32); }
       for (int q = 0; q < NP; q++) mbar_init(&S.inbar[u][q], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -142,64 +142,85 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
   uint32_t k = 0;
 
   if (consumer) {
+    // Ring slot k lives in stage k % NS and belongs to consumer warp k % NCW.  With two consumer warps (NS even) the
+    // even and the odd slots are two independent pipelines -- each warp waits only on the barriers of its own stages,
+    // so it observes every one of their phases (a parity wait means nothing to a waiter that skips phases: an earlier
+    // version let both warps wait on the flush slot and a warp that had drifted ahead took an older phase of the same
+    // parity for it).  The pipelines meet at a flush, which therefore takes TWO consecutive slots, one in each:
+    //   slot kA -> the "giver" (warp kA % 2): dumps its accumulators into stage A, restarts from zero;
+    //   slot kB = kA + 1 -> the "taker": adds the dump (xfer barrier of stage A, phase tracked by counting flushes per
+    //   stage), releases stage A, flushes through stage B and carries the cumulative amplitude from there on.
+    static_assert(NCW == 1 || (NCW == 2 && NS % 2 == 0), "one or two consumer warps");
     ThreadState<C> st;
-    uint32_t xph = 0u;                 // per-stage phase bits of the hand-over barriers (a stage cannot be handed over
-    while (w.next(P, it)) {             // twice before warp 0 has released it, so its barrier never runs ahead)
-      const int sgi = (int)(k % (uint32_t)NS);
-      const uint32_t par = (k / (uint32_t)NS) & 1u;
+    uint32_t xph = 0u;                 // per-stage phase bits of the hand-over barriers
+    auto flush_through = [&](double* buf, uint32_t iSnap) {
+      // fragment layout -> one tile per lane (through the handed-over stage), common flush code, and back (snapshots
+      // are cumulative)
+      ws_store_frag<C>(buf, lane, st);
+      __syncwarp();
+      ws_load_tile<C>(buf, lane, st);
+      flush_lane<C>(P, g, w.tv, pc, iSnap, lane, &st);
+      ws_store_tile<C>(buf, lane, st);
+      __syncwarp();
+      ws_load_frag<C>(buf, lane, st);
+      __syncwarp();
+    };
+    while (w.next(P, it)) {
       if (it.newTrack) {
 #pragma unroll
         for (int q = 0; q < C::NACC; q++) st.acc[q] = 0.0;
       }
-      WsStage<C>& sg = S.stage[u][sgi];
-      // EVERY consumer warp passes EVERY item's full barrier and arrives on its empty barrier (count 32 * NCW), whether
-      // it processes the item or not: a parity wait is only meaningful for a waiter that observes each phase, and a
-      // stage must not be refilled before both warps are past it -- otherwise the even and the odd items form two
-      // independent pipelines (stage = k % NS, warp = k % NCW) that drift apart and a late warp mistakes an earlier or
-      // later phase of the same parity for its own (seen as whole directions going wrong in some runs).
-      mbar_wait(&S.full[u][sgi], par);
+      const int sgi = (int)(k % (uint32_t)NS);
+      const uint32_t par = (k / (uint32_t)NS) & 1u;
       if (it.kind == 0) {
-        if ((int)(k % (uint32_t)NCW) == cidx) ws_main<C>(P, g, sg, lane, st);
-        mbar_arrive(&S.empty[u][sgi]);
-      } else {
-        double* buf = reinterpret_cast<double*>(&sg);
-        if (NCW > 1 && cidx == 1) {
-          // hand this warp's sums to warp 0 (same fragment layout, lane-major) and restart from zero: warp 0 carries
-          // the cumulative amplitude from here on (snapshots are cumulative)
-#pragma unroll
-          for (int q = 0; q < C::NACC; q++) { buf[q * 32 + lane] = st.acc[q]; st.acc[q] = 0.0; }
-          mbar_arrive(&S.xfer[u][sgi]);
-          mbar_arrive(&S.empty[u][sgi]);
-        } else {
-          if (NCW > 1) {
-            mbar_wait(&S.xfer[u][sgi], (xph >> sgi) & 1u);
-            xph ^= 1u << sgi;
-#pragma unroll
-            for (int q = 0; q < C::NACC; q++) st.acc[q] += buf[q * 32 + lane];
-            __syncwarp();
-          }
-          // flush: fragment layout -> one tile per lane (through the handed-over stage), common flush code, and back
-          ws_store_frag<C>(buf, lane, st);
-          __syncwarp();
-          ws_load_tile<C>(buf, lane, st);
-          flush_lane<C>(P, g, w.tv, pc, it.iSnap, lane, &st);
-          ws_store_tile<C>(buf, lane, st);
-          __syncwarp();
-          ws_load_frag<C>(buf, lane, st);
-          __syncwarp();
+        if ((int)(k % (uint32_t)NCW) == cidx) {
+          mbar_wait(&S.full[u][sgi], par);
+          ws_main<C>(P, g, S.stage[u][sgi], lane, st);
           mbar_arrive(&S.empty[u][sgi]);
         }
+        k++;
+      } else if (NCW == 1) {
+        mbar_wait(&S.full[u][sgi], par);
+        flush_through(reinterpret_cast<double*>(&S.stage[u][sgi]), it.iSnap);
+        mbar_arrive(&S.empty[u][sgi]);
+        k++;
+      } else {
+        const int sgB = (int)((k + 1u) % (uint32_t)NS);
+        double* bufA = reinterpret_cast<double*>(&S.stage[u][sgi]);
+        if ((int)(k % 2u) == cidx) {               // giver
+          mbar_wait(&S.full[u][sgi], par);
+#pragma unroll
+          for (int q = 0; q < C::NACC; q++) { bufA[q * 32 + lane] = st.acc[q]; st.acc[q] = 0.0; }
+          mbar_arrive(&S.xfer[u][sgi]);
+        } else {                                   // taker
+          mbar_wait(&S.full[u][sgB], ((k + 1u) / (uint32_t)NS) & 1u);
+          mbar_wait(&S.xfer[u][sgi], (xph >> sgi) & 1u);
+#pragma unroll
+          for (int q = 0; q < C::NACC; q++) st.acc[q] += bufA[q * 32 + lane];
+          mbar_arrive(&S.empty[u][sgi]);
+          flush_through(reinterpret_cast<double*>(&S.stage[u][sgB]), it.iSnap);
+          mbar_arrive(&S.empty[u][sgB]);
+        }
+        xph ^= 1u << sgi;
+        k += 2u;
       }
-      k++;
     }
     return;
   }
 
   // ---- producer pidx of unit u: items k with k % NP == pidx
   struct Own { uint32_t kind, base, k, itStart; int cnt; uint64_t idx; bool valid; };   // idx: element of step `base` in the arrays
+  bool flush2 = false;               // two consumer warps: a flush takes two consecutive ring slots (see above)
   auto next_own = [&](Own& o) {
-    while (w.next(P, it)) {
+    for (;;) {
+      if (flush2) {
+        flush2 = false;
+        const uint32_t kk = k++;
+        if (kk % (uint32_t)NP == (uint32_t)pidx) { o.kind = 1u; o.base = 0u; o.cnt = 0; o.k = kk; o.idx = 0; o.valid = true; return; }
+      }
+      if (!w.next(P, it)) { o.valid = false; return; }
       const uint32_t kk = k++;
+      if (it.kind == 1u && NCW > 1) flush2 = true;
       if (kk % (uint32_t)NP == (uint32_t)pidx) {
         o.kind = it.kind; o.base = it.base; o.cnt = it.cnt; o.k = kk; o.itStart = w.tv.itStart;
         o.idx = (uint64_t)((const double*)w.tv.x - (const double*)P.x) + it.base;
@@ -207,7 +228,6 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
         return;
       }
     }
-    o.valid = false;
   };
   const uint64_t totalSteps = P.offsets[P.nTracks];
   // Staged inputs of the sub-batch whose first step is element idx: the 34 packed records (k_prepass: x, y, z, a, b per
