@@ -45,9 +45,10 @@ GRID = (256, 32, 32)
 KIND_NAMES = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair, DFMA'}
 
 
-def kernel_label(info, fp64):
-    """k_integrate<...> as reported by srb_last_launch: the fp64 pair kernel runs on DMMA when tile width x components % 8 == 0"""
-    kind, tw, nc = int(info.kind), int(info.tile_width), int(info.n_components)
+def kernel_label(info, fp64, kind=None):
+    """k_integrate<...> as reported by srb_last_launch (kind: Result.kind, the on-device choice when phasor='auto'): the
+    fp64 pair kernel runs on DMMA when tile width x components % 8 == 0"""
+    kind, tw, nc = int(info.kind if kind is None else kind), int(info.tile_width), int(info.n_components)
     name = 'pair, DMMA' if (kind == 3 and fp64 and (tw * nc) % 8 == 0) else KIND_NAMES[kind]
     return 'k_integrate<%s, tile %d>' % (name, tw)
 
@@ -315,6 +316,7 @@ def run_product(a):
     cnt = counters.cpu().numpy()
     guard_pass = float(cnt[0]) / max(float(cnt[1]), 1.0)
     checksum = float(last.spectra[0].sum().item())
+    kind_run = last.kind
     del last
 
     # ---------------- fp32 block (rank 0 of a single-GPU run): both float modes on the same recipe
@@ -334,7 +336,7 @@ def run_product(a):
             upd32 = np32 * (n_s - 1) * nodes
             rate = upd32 / (k_ms32 * 1e-3)
             fp32[mode] = {
-                'value': rate, 'unit': 'updates/s', 'kernel': kernel_label(res32.info, False),
+                'value': rate, 'unit': 'updates/s', 'kernel': kernel_label(res32.info, False, res32.kind),
                 'what': {'mixed': "dtype='float' default: fp64 tracks/tables/per-step work, fp32 per-omega phasor + accumulate "
                                   '(judged against the fp64 oracle, <= 1e-4)',
                          'literal': "dtype='float', float_mode='literal': every operation of the reference kernels in fp32 "
@@ -378,7 +380,7 @@ def run_product(a):
                   'checker_port_bit_identical_to_reference_kernels': bool(np.array_equal(port['radiation']['total'], want)),
                   'checker': strict_lib + (' (the reference\'s own kernels, g++ -O2 -ffp-contract=off)' if strict_lib == 'ref_strict'
                                            else ' (oracle port, strict build)'),
-                  'kernel': kernel_label(resp.info, a.dtype == 'double'),
+                  'kernel': kernel_label(resp.info, a.dtype == 'double', resp.kind),
                   'sample': f'{npar} particle(s) x {n_s} samples x {GRID[0]}x{GRID[1]}x{GRID[2]} nodes = the CPU arm\'s first '
                             f'particles, full bench shape, phasor={a.phasor}; checker {dt_strict:.1f} s'}
         del resp, dbatch
@@ -464,11 +466,11 @@ def run_product(a):
     achieved = updates_rank * slots_alg / (k_ms * 1e-3)          # algorithmic slots/s of one launch
     issued = None
     tw, nc = int(info.tile_width), int(info.n_components)
-    if int(info.kind) == 1:      # recurrence: per lane and step (TW-2) chain + NC*TW accumulate + 2 seed ops, for TW half-updates
+    if kind_run == 1:      # recurrence: per lane and step (TW-2) chain + NC*TW accumulate + 2 seed ops, for TW half-updates
         issued = 2.0 * ((tw - 2) + nc * tw + 2) / tw
-    elif int(info.kind) in (3, 4):   # pair: per lane and step 4 (X = Y*Z) + 4*NC*TW/2 accumulate FMAs, for TW updates;
+    elif kind_run in (3, 4):   # pair: per lane and step 4 (X = Y*Z) + 4*NC*TW/2 accumulate FMAs, for TW updates;
         issued = (4 + 2 * nc * tw) / tw   # fp64 with TW*NC % 8 == 0: the accumulate FMAs are issued as DMMA.8x8x4 (256 each)
-    kernel_name = kernel_label(info, a.dtype == 'double')
+    kernel_name = kernel_label(info, a.dtype == 'double', kind_run)
     kname = kernel_name[len('k_integrate<'):].rsplit(',', 1)[0]
     ev, ev_src = ncu_evidence(kernel_name, n_p, n_s)
     roofline = {

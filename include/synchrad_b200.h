@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SRB_ABI_VERSION 1
+#define SRB_ABI_VERSION 2
 
 /* mode: which kernel file of the reference is replaced (calc.py:617-620) */
 #define SRB_MODE_FAR 0  /* kernel_farfield.cl  */
@@ -58,8 +58,9 @@ extern "C" {
 #define SRB_DTYPE_F32_LITERAL 2
 
 /* phasor: how exp(i*omega*tau) is evaluated per node */
-#define SRB_PHASOR_AUTO 0   /* uniform grid: pair kernel (far, non-spheric) or recurrence, chosen from a sampled
-                               Nyquist-guard statistic (one 12-byte read-back synchronises the stream); else direct */
+#define SRB_PHASOR_AUTO 0   /* uniform grid: pair kernel (far field) or recurrence, chosen ON THE DEVICE from a sampled
+                               Nyquist-guard statistic (both are enqueued, the other returns at once; no host
+                               synchronisation; choice reported in counters[2]); else direct */
 #define SRB_PHASOR_DIRECT 1 /* per-node sincos of the reference's rounded phase */
 #define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
 #define SRB_PHASOR_PAIR 3   /* symmetric node pairs about the tile centre, broadcast pair phasors (uniform grids, far
@@ -67,6 +68,9 @@ extern "C" {
                                (DMMA.8x8x4) when tile width x components is a multiple of 8 */
 #define SRB_PHASOR_PAIR_FMA 4 /* the pair kernel with the accumulation kept on the scalar FP64 pipe (DFMA) */
 /* (5 was the experimental gridding kernel of round 1; removed, see profiles/r02_spread_v2_decision.txt) */
+
+/* srb_launch_info.kind when the kernel was chosen on the device (read counters[2]) */
+#define SRB_KIND_ON_DEVICE (-1)
 
 /* Spectral grid + run constants: the `args_axes + args_res + args_aux` of calc.py:306-322.
  * Tables are float64 arrays with the content `_init_data` uploads (calc.py:486-512): omega is
@@ -127,7 +131,10 @@ size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks);
  *   spectra[n_spectra] : float64 device buffers, each nSnaps*nPhi*nAxis2*nOmega, `+=`
  *   scratch            : device buffer of >= srb_scratch_bytes() (may be NULL if that is 0);
  *                        a smaller buffer is accepted and only reduces parallelism
- *   counters           : device uint64[2] or NULL; zeroed and filled by the call */
+ *   counters           : device uint64[4] or NULL; zeroed and filled by the call: [0] updates that passed the Nyquist
+ *                        guard, [1] updates visited, [2] with phasor = AUTO and two eligible kernels: the kind chosen
+ *                        on the device (srb_launch_info.kind == SRB_KIND_ON_DEVICE then), [3] reserved
+ * Asynchronous with respect to the host on `stream`: no call of this library synchronises the stream. */
 int srb_integrate(const srb_grid* grid, const srb_tracks* tracks, double* const* spectra,
                   int n_spectra, void* scratch, size_t scratch_bytes, uint64_t* counters,
                   void* stream);

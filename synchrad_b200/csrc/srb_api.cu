@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NW * 32, min_blocks<C>()) k_integrate(const sr
   const uint32_t nVDtiles = (P.nVD + NW - 1) / NW;
   const uint32_t vd = (blockIdx.x % nVDtiles) * NW + warp;   // neighbouring blocks share the tracks
   const uint32_t pc = blockIdx.x / nVDtiles;
-  if (vd >= P.nVD) return;
+  if (vd >= P.nVD || srb::deselected(P)) return;
   srb::ThreadState<C> st;
   srb::warp_task<C>(P, vd, pc, *sm, &st);
 }
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
   // producer = k % NP that holds iff each stage is always served by the same producer
   static_assert(NS % NP == 0, "ring stages must map to a fixed producer");
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+  if (deselected(P)) return;           // (uniform over the block: before any barrier)
   // masked steps of the tensor-core stream multiply stale stage data by 0: keep it finite from the start
   for (uint32_t k = threadIdx.x; k < sizeof(S.stage) / 4u; k += blockDim.x) reinterpret_cast<uint32_t*>(&S.stage)[k] = 0u;
   if (threadIdx.x == 0) {
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
 // far: a = (beta_{it+1}-beta_it)/dt and b = (beta_{it+1}+beta_it)/2 ; near: beta_it.
 // Same strict operation order as the in-kernel path, so results are bit-identical.
 __global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_t total, uint64_t stride) {
+  if (srb::deselected(P)) return;
   const double dtInv = srb::sdiv(1.0, P.dt);
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t a = 0, b = P.nTracks;          // last track with offsets[t] <= i
@@ -366,8 +368,18 @@ __global__ void k_probe(const srb::Params P, uint64_t total, double wFirst, doub
   else if (wFirst * dtau < 3.14159265358979323846) atomicAdd(out + 2, 1u);
 }
 
+// phasor = AUTO: the decision from the probe counts, on the device (no host round trip): partial steps cost the pair
+// kernel ~3x, so it is taken only when they are < 10 % of the all-pass ones.  sel[0] = chosen kind; the same code is
+// left in counters[2] for the caller.
+__global__ void k_decide(const unsigned int* probe, int32_t* sel, unsigned long long* counters) {
+  const bool preferRecur = probe[0] > 0 && (double)probe[2] > 0.1 * (double)probe[1];
+  sel[0] = preferRecur ? srb::KIND_RECUR : srb::KIND_PAIR;
+  if (counters) counters[2] = (unsigned long long)sel[0];
+}
+
 // out[c][i] += sum over particle chunks of the private partial spectra (fixed order: deterministic)
 __global__ void k_reduce_slabs(srb::Params P, int nOut, size_t perOut) {
+  if (srb::deselected(P)) return;
   const size_t n = (size_t)nOut * perOut;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double acc = 0.0;
@@ -681,45 +693,17 @@ int srb_num_spectra(int mode, int comp) {
 
 size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks) {
   if (validate(grid, tracks) != 0) return 0;
-  Plan p;
-  if (make_plan(grid, tracks, 0, true, &p) != 0) return 0;
-  return ((size_t)(p.nPC - 1) * p.slabDoubles + p.preDoubles) * sizeof(double);
+  Plan p, q;
+  if (make_plan(grid, tracks, 0, true, &p, false) != 0) return 0;
+  if (make_plan(grid, tracks, 0, true, &q, true) != 0) return 0;
+  const size_t a = ((size_t)(p.nPC - 1) * p.slabDoubles + p.preDoubles) * sizeof(double);
+  const size_t b = ((size_t)(q.nPC - 1) * q.slabDoubles + q.preDoubles) * sizeof(double);
+  return 64 + std::max(a, b);        // 64-byte header: guard probe counts + on-device kernel choice (phasor = AUTO)
 }
 
-int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int n_spectra,
-                  void* scratch, size_t scratch_bytes, uint64_t* counters, void* stream_) {
-  if (validate(g, t) != 0) return -1;
-  cudaStream_t stream = (cudaStream_t)stream_;
-  // Both uniform-grid kernels eligible: sample the guard statistics (one small kernel + a 12-byte read-back,
-  // the only host synchronisation of this call; an explicit `phasor` avoids it)
-  bool preferRecur = false;
-  {
-    const bool spheric = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
-    const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
-    unsigned int* probeBuf = (scratch && scratch_bytes >= 64) ? (unsigned int*)scratch : (unsigned int*)counters;
-    if (g->phasor == SRB_PHASOR_AUTO && uniform && g->mode == SRB_MODE_FAR && g->dtype != SRB_DTYPE_F32_LITERAL &&
-        probeBuf && t->nTracks && t->totalSteps_host > 2) {
-      srb::Params Q;
-      std::memset(&Q, 0, sizeof Q);
-      Q.nA2 = g->nAxis2; Q.nPhi = g->nPhi; Q.axA = g->sinTheta; Q.axB = g->cosTheta; Q.sinPhi = g->sinPhi; Q.cosPhi = g->cosPhi;
-      Q.dt = g->dt; Q.nTracks = t->nTracks; Q.x = t->x; Q.y = t->y; Q.z = t->z; Q.offsets = t->offsets;
-      unsigned int h[3] = {0, 0, 0};
-      SRB_CUDA(cudaMemsetAsync(probeBuf, 0, 16, stream));
-      k_probe<<<64, 128, 0, stream>>>(Q, t->totalSteps_host, g->omega_first_host, g->omega_last_host, probeBuf);
-      SRB_CUDA(cudaGetLastError());
-      SRB_CUDA(cudaMemcpyAsync(h, probeBuf, 12, cudaMemcpyDeviceToHost, stream));
-      SRB_CUDA(cudaStreamSynchronize(stream));
-      preferRecur = h[0] > 0 && (double)h[2] > 0.1 * (double)h[1];   // partial steps cost the pair kernel ~3x
-    }
-  }
-  Plan p;
-  if (make_plan(g, t, scratch ? scratch_bytes : 0, false, &p, preferRecur) != 0) return -1;
-  if (n_spectra != p.nOut || !spectra) return fail("n_spectra does not match comp");
-  for (int c = 0; c < p.nOut; c++) if (!spectra[c]) return fail("null spectrum buffer");
-  std::memset(&g_info, 0, sizeof g_info);
-  if (counters) SRB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(uint64_t), stream));
-  if (t->nTracks == 0) return 0;
-
+// one plan's launches: [pre-pass] [zero the private partial spectra] kernel [reduce]; `sel`/`want`: see Params::sel
+static int launch_plan(const srb_grid* g, const srb_tracks* t, const Plan& p, double* const* spectra, void* scratch,
+                       uint64_t* counters, cudaStream_t stream, const int32_t* sel, int want, uint32_t* launched) {
   srb::Params P;
   std::memset(&P, 0, sizeof P);
   P.mode = g->mode; P.comp = g->comp;
@@ -739,34 +723,87 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
   for (int c = 0; c < p.nOut; c++) P.out[c] = spectra[c];
   double* preBuf = p.preDoubles ? (double*)scratch : nullptr;
   P.pre = preBuf; P.preStride = (t->totalSteps_host + 1) & ~(uint64_t)1;
-  // TMA bulk copies need 16-byte aligned sources: the arrays themselves must be (torch allocations are)
+  // TMA bulk copies need 16-byte aligned sources
   P.tmaOK = (((uintptr_t)preBuf & 15u) == 0 && !std::getenv("SRB_WS_NOTMA")) ? 1 : 0;      // (env: debugging aid)
   P.prePacked = p.ws ? 1 : 0;
   P.slabs = (double*)scratch + p.preDoubles; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
   P.counters = (unsigned long long*)counters;
-  uint32_t launched = 0;
+  P.sel = sel; P.selWant = want;
   if (preBuf) {
     const uint64_t total = t->totalSteps_host;
     const int pb = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)p.numSM * 16);
     k_prepass<<<pb, 256, 0, stream>>>(P, preBuf, total, P.preStride);
     SRB_CUDA(cudaGetLastError());
-    launched++;
+    (*launched)++;
   }
   if (p.nPC > 1) SRB_CUDA(cudaMemsetAsync(P.slabs, 0, (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double), stream));
   const uint32_t blocks = p.nVDtiles * p.nPC;
   p.L.kernel<<<blocks, p.L.threads, p.L.smem, stream>>>(P);
   SRB_CUDA(cudaGetLastError());
-  launched++;
+  (*launched)++;
   if (p.nPC > 1) {
     const size_t n = p.slabDoubles;
     const int rb = (int)std::min<size_t>((n + 255) / 256, (size_t)p.numSM * 8);
     k_reduce_slabs<<<rb, 256, 0, stream>>>(P, p.nOut, p.perOut);
     SRB_CUDA(cudaGetLastError());
-    launched++;
+    (*launched)++;
   }
-  g_info.kind = p.kind; g_info.tile_width = p.tw; g_info.chunk_nodes = p.chunkNodes; g_info.n_chunks = p.nChunks;
-  g_info.n_virtual_dirs = p.nVD; g_info.n_particle_chunks = p.nPC; g_info.grid_blocks = blocks;
-  g_info.block_threads = (uint32_t)p.L.threads; g_info.n_components = (uint32_t)p.nc; g_info.smem_bytes = (uint32_t)p.L.smem; g_info.kernels_launched = launched;
+  return 0;
+}
+
+static void fill_info(const Plan& p, uint32_t launched, int kind) {
+  g_info.kind = kind; g_info.tile_width = p.tw; g_info.chunk_nodes = p.chunkNodes; g_info.n_chunks = p.nChunks;
+  g_info.n_virtual_dirs = p.nVD; g_info.n_particle_chunks = p.nPC; g_info.grid_blocks = p.nVDtiles * p.nPC;
+  g_info.block_threads = (uint32_t)p.L.threads; g_info.n_components = (uint32_t)p.nc; g_info.smem_bytes = (uint32_t)p.L.smem;
+  g_info.kernels_launched = launched;
+}
+
+int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int n_spectra,
+                  void* scratch, size_t scratch_bytes, uint64_t* counters, void* stream_) {
+  if (validate(g, t) != 0) return -1;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nOut = srb_num_spectra(g->mode, g->comp);
+  if (n_spectra != nOut || !spectra) return fail("n_spectra does not match comp");
+  for (int c = 0; c < nOut; c++) if (!spectra[c]) return fail("null spectrum buffer");
+  std::memset(&g_info, 0, sizeof g_info);
+  if (counters) SRB_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(uint64_t), stream));
+  if (t->nTracks == 0) return 0;
+  uint32_t launched = 0;
+  // phasor = AUTO with both uniform-grid kernels eligible (far field): the pair kernel is faster on all-pass steps but
+  // ~3x slower on partially passing ones, so a probe kernel samples the Nyquist-guard statistics of 8192 random
+  // (track, step, direction) triples and the choice is made ON THE DEVICE: both candidates are enqueued and the one
+  // that was not chosen returns at once.  No host synchronisation; the choice is left in counters[2].
+  const bool uniform = g->omega_uniform && g->nOmega >= 2 && g->omega_last_host > g->omega_first_host;
+  if (g->phasor == SRB_PHASOR_AUTO && uniform && g->mode == SRB_MODE_FAR && g->dtype != SRB_DTYPE_F32_LITERAL &&
+      scratch && scratch_bytes >= 256 && t->totalSteps_host > 2) {
+    unsigned int* probeBuf = (unsigned int*)scratch;              // 64-byte header of the scratch: probe counts, decision
+    int32_t* sel = (int32_t*)scratch + 8;
+    void* body = (char*)scratch + 64;
+    Plan pPair, pRec;
+    if (make_plan(g, t, scratch_bytes - 64, false, &pPair, false) != 0) return -1;
+    if (make_plan(g, t, scratch_bytes - 64, false, &pRec, true) != 0) return -1;
+    if (pPair.kind != pRec.kind) {
+      srb::Params Q;
+      std::memset(&Q, 0, sizeof Q);
+      Q.nA2 = g->nAxis2; Q.nPhi = g->nPhi; Q.axA = g->sinTheta; Q.axB = g->cosTheta; Q.sinPhi = g->sinPhi; Q.cosPhi = g->cosPhi;
+      Q.dt = g->dt; Q.nTracks = t->nTracks; Q.x = t->x; Q.y = t->y; Q.z = t->z; Q.offsets = t->offsets;
+      SRB_CUDA(cudaMemsetAsync(probeBuf, 0, 64, stream));
+      k_probe<<<64, 128, 0, stream>>>(Q, t->totalSteps_host, g->omega_first_host, g->omega_last_host, probeBuf);
+      k_decide<<<1, 1, 0, stream>>>(probeBuf, sel, (unsigned long long*)counters);
+      SRB_CUDA(cudaGetLastError());
+      launched += 2;
+      // the two candidates share the scratch body (only one of them runs): zero both slab regions first, then the
+      // (conditional) pre-passes, kernels and reductions
+      if (launch_plan(g, t, pPair, spectra, body, counters, stream, sel, pPair.kind, &launched) != 0) return -1;
+      if (launch_plan(g, t, pRec, spectra, body, counters, stream, sel, pRec.kind, &launched) != 0) return -1;
+      fill_info(pPair, launched, SRB_KIND_ON_DEVICE);
+      return 0;
+    }
+  }
+  Plan p;
+  if (make_plan(g, t, scratch ? scratch_bytes : 0, false, &p, false) != 0) return -1;
+  if (launch_plan(g, t, p, spectra, scratch, counters, stream, nullptr, 0, &launched) != 0) return -1;
+  fill_info(p, launched, p.kind);
   return 0;
 }
 
@@ -879,7 +916,7 @@ int srb_integrate_host(const srb_grid* g, const srb_tracks* t, double* const* sp
   void* scratch = nullptr;
   if (sb) { if (cudaMalloc(&scratch, sb) == cudaSuccess) owned.push_back(scratch); else { scratch = nullptr; sb = 0; cudaGetLastError(); } }
   uint64_t* dcnt = nullptr;
-  if (counters_host) { if (cudaMalloc((void**)&dcnt, 16) == cudaSuccess) owned.push_back(dcnt); else dcnt = nullptr; }
+  if (counters_host) { if (cudaMalloc((void**)&dcnt, 32) == cudaSuccess) owned.push_back(dcnt); else dcnt = nullptr; }
   int rc = srb_integrate(&gd, &td, dsp.data(), nOut, scratch, sb, dcnt, nullptr);
   if (rc == 0) {
     std::vector<double> h(per);

@@ -251,7 +251,12 @@ struct Params {
   uint64_t preStride;
   int32_t tmaOK;        // pre is 16-byte aligned (TMA staging of srb_ws.cuh)
   int32_t prePacked;    // pre holds one 9-double record per step: x, y, z, a0..a2, b0..b2 (warp-specialised kernel)
+  // phasor = AUTO with two eligible kernels: both are launched and the one the device-side guard probe did not
+  // select returns at once (sel == nullptr: unconditional)
+  const int32_t* sel;
+  int32_t selWant;
 };
+SRB_HD bool deselected(const Params& P) { return P.sel != nullptr && *P.sel != P.selWant; }
 
 // NC: amplitude components carried per node in far-field mode.
 //   3 — Cartesian (or, for the spheric kernels, the (n, e_theta, e_phi) projections);

@@ -56,7 +56,14 @@ class DeviceGrid:
 
 
 class Result:
-    __slots__ = ('spectra', 'counters', 'info', 'updates', 'elapsed_ms', '_keep')
+    __slots__ = ('spectra', 'counters', 'info', 'updates', 'elapsed_ms', '_keep', '_kind_dev')
+
+    @property
+    def kind(self):
+        """SRB_KIND_* of the kernel that ran.  With phasor='auto' and two eligible kernels the library chooses on the
+        device without a host round trip (include/synchrad_b200.h: SRB_KIND_ON_DEVICE); reading it here synchronises."""
+        k = int(self.info.kind)
+        return int(self._kind_dev.item()) if k < 0 and self._kind_dev is not None else k
 
 
 def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='auto',
@@ -144,7 +151,7 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
                     break
                 except torch.cuda.OutOfMemoryError:
                     torch.cuda.empty_cache()
-        cnt = torch.zeros(2, dtype=torch.int64, device=dev) if counters else None
+        cnt = torch.zeros(4, dtype=torch.int64, device=dev) if counters else None
         if timing:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -163,6 +170,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
             res.elapsed_ms = e0.elapsed_time(e1)
         info = _lib.srb_launch_info()
         lib.srb_last_launch(ctypes.byref(info))
+        res._kind_dev = cnt[2:3].clone() if cnt is not None else None
+        if cnt is not None:
+            cnt = cnt[:2]                       # [passed, visited]; slot 2 is the on-device kernel choice (see Result.kind)
         if counters_into is not None and cnt is not None:
             counters_into += cnt
             cnt = counters_into

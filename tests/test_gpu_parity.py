@@ -451,7 +451,7 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
 
 def test_scratch_size_only_changes_parallelism(cuda_lib):
     """srb_integrate accepts any scratch size: none (one particle chunk, kinematics computed in-kernel),
-    partial, full (pre-pass planes + private partial spectra).  Same spectrum (to summation order)."""
+    partial, full (pre-pass records / planes + private partial spectra).  Same spectrum (to summation order)."""
     import torch
     from synchrad_b200 import _lib, engine, host
     tracks, dt = cases.c5_tracks_numpy(30, 300)
@@ -460,17 +460,45 @@ def test_scratch_size_only_changes_parallelism(cuda_lib):
     dev = torch.device('cuda', 0)
     grid = engine.DeviceGrid(args, dtype, dev)
     pk = host.pack_tracks(tracks, [t[6] for t in tracks], np.double, None, 1)
-    full = engine.integrate(args, dtype, grid, pk, 'total', 1)
+    full = engine.integrate(args, dtype, grid, pk, 'total', 1, phasor='pair')
     ref = full.spectra[0].cpu().numpy()
     assert full.info.n_particle_chunks > 1 and full.info.kernels_launched == 3       # pre-pass, integrate, reduce
-    want = cuda_lib.srb_scratch_bytes  # noqa: F841  (size query is exercised inside engine.integrate)
-    for limit in (0, 3 * ref.nbytes, 6 * 8 * pk.total + 2 * ref.nbytes):
-        res = engine.integrate(args, dtype, grid, pk, 'total', 1, max_scratch_bytes=limit)
+    assert full.info.block_threads == 512               # warp-specialised form: 2 consumer + 2 producer warps x 4 directions
+    for limit in (0, 3 * ref.nbytes, 6 * 8 * pk.total + 2 * ref.nbytes, 9 * 8 * pk.total + 16 + 2 * ref.nbytes):
+        res = engine.integrate(args, dtype, grid, pk, 'total', 1, phasor='pair', max_scratch_bytes=limit)
         got = res.spectra[0].cpu().numpy()
         assert max(rel_errors(got, ref)) < 1e-13, limit
         if limit == 0:
             assert res.info.n_particle_chunks == 1 and res.info.kernels_launched == 1
-        elif limit == 3 * ref.nbytes:                    # too small for the pre-pass planes: slabs only
+        elif limit == 3 * ref.nbytes:                    # too small for any pre-pass: slabs only
             assert res.info.n_particle_chunks == 4 and res.info.kernels_launched == 2
-        else:                                            # pre-pass + 2 private spectra
+        elif limit == 6 * 8 * pk.total + 2 * ref.nbytes:   # room for the 6 planes but not for the packed records: the
+            assert res.info.block_threads == 128           # warp-autonomous form of the pair kernel, 2 private spectra
             assert res.info.n_particle_chunks == 3 and res.info.kernels_launched == 3
+        else:                                            # packed records + 2 private spectra: warp-specialised form
+            assert res.info.block_threads == 512
+            assert res.info.n_particle_chunks == 3 and res.info.kernels_launched == 3
+
+
+def test_auto_choice_is_made_on_the_device(cuda_lib, oracle):
+    """phasor='auto' with both uniform-grid kernels eligible: a probe kernel samples the guard statistics, the choice
+    is made on the device (both candidates enqueued, one returns at once) -- srb_integrate never synchronises the
+    stream; the choice is reported through counters[2]."""
+    import torch
+    from synchrad_b200 import engine, host
+    dev = torch.device('cuda', 0)
+    for maker, want in ((lambda: cases.c5_tracks_numpy(12, 400) + (None,), 3), (lambda: cases.wiggler_tracks(12, 256), 1)):
+        tracks, dt, info = maker()
+        a = cases.c5_args(grid=(256, 4, 4)) if info is None else cases.wiggler_args(info, grid=(256, 4, 4))
+        args, dtype = host.init_args(a)
+        args['timeStep'] = dt
+        grid = engine.DeviceGrid(args, dtype, dev)
+        pk = host.pack_tracks(tracks, [t[6] for t in tracks], np.double, None, 1)
+        res = engine.integrate(args, dtype, grid, pk, 'total', 1, phasor='auto')
+        assert int(res.info.kind) == -1 and res.kind == want          # SRB_KIND_ON_DEVICE; all-pass -> pair, guard-dominated -> recurrence
+        assert res.info.kernels_launched == 8                         # probe, decide, 2 x (pre-pass, integrate, reduce)
+        ref = oracle.calculate_spectrum(a, tracks, dt)
+        got = np.ascontiguousarray(res.spectra[0].cpu().numpy().swapaxes(-1, -3))
+        assert max(rel_errors(got, ref['radiation']['total'])) < 1e-9
+        cnt = res.counters.cpu().numpy()
+        assert cnt[0] == ref['passed'] and cnt[1] == ref['updates']

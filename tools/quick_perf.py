@@ -35,6 +35,6 @@ for r in range(reps + 1):
     if r:
         best = min(best, res.elapsed_ms)
 i = res.info
-sys.__stdout__.write(f"mode={mode} comp={comp} native={bool(os.environ.get('NATIVE'))} grid={grid} lib={os.environ.get('SYNCHRAD_B200_LIB','default')} {dtype} {phasor} kind={i.kind} tw={i.tile_width} "
+sys.__stdout__.write(f"mode={mode} comp={comp} native={bool(os.environ.get('NATIVE'))} grid={grid} lib={os.environ.get('SYNCHRAD_B200_LIB','default')} {dtype} {phasor} kind={res.kind} tw={i.tile_width} "
                      f"pc={i.n_particle_chunks} blocks={i.grid_blocks} thr={i.block_threads} smem={i.smem_bytes} "
                      f"ms={best:.2f} updates/s={upd / best * 1e3:.4e} checksum={float(res.spectra[0].sum()):.10e}\n")
