@@ -193,7 +193,13 @@ class SynchRad(Utilities):
                         print('it_range from the input file will be used')
                 elif self.rank == 0 and verbose:
                     print('Separate it_range for each track will be used')
-            index = host.select_tracks(int(n_file), Np_max, self.rank, self.size)
+            partition = self.Args.get('partition', 'round_robin')
+            lengths = None
+            if partition == 'balanced' and self.size > 1:     # needs every track's length: headers of the first Np tracks
+                n_sel = int(n_file) if Np_max is None else min(int(Np_max), int(n_file))
+                with trackio.TrackSource(file_tracks, range(n_sel)) as all_tracks:
+                    lengths = [t.n for t in all_tracks.tracks]
+            index = host.select_tracks(int(n_file), Np_max, self.rank, self.size, lengths, partition)
             # headers only: the samples go from the file straight into the pinned SoA buffers when the
             # batches are packed below (the reference holds every local track in host RAM, calc.py:210-216)
             track_source = trackio.TrackSource(file_tracks, index)
@@ -206,7 +212,9 @@ class SynchRad(Utilities):
         else:
             if it_range is None and self.rank == 0 and verbose:
                 print('Separate it_range for each track will be used')
-            index = host.select_tracks(len(particleTracks), Np_max, self.rank, self.size)
+            partition = self.Args.get('partition', 'round_robin')
+            lengths = [host.track_length(t) for t in particleTracks] if partition == 'balanced' and self.size > 1 else None
+            index = host.select_tracks(len(particleTracks), Np_max, self.rank, self.size, lengths, partition)
             particleTracks = [particleTracks[i] for i in index]
         if 'timeStep' not in self.Args:
             raise ValueError('timeStep is required (c*dt in the units of the coordinates)')
@@ -214,7 +222,7 @@ class SynchRad(Utilities):
             self._set_snap_iterations(it_range, nSnaps)
 
         dt64 = getattr(self, '_timeStep64', float(self.Args['timeStep']))
-        run = dict(native=self._native, phasor=self._phasor, timing=True, timeStep=dt64)
+        run = dict(native=self._native, phasor=self._phasor, timing='events', timeStep=dt64)
         if isinstance(particleTracks, host.PackedTracks):
             packed = particleTracks
             if weights_normalize is not None or Np_max is not None:
@@ -240,6 +248,10 @@ class SynchRad(Utilities):
             spans = host.split_batches(lengths, max(int(budget) // 96, 1))
             batches = spans
         res, h2d, upd, ms = None, 0, 0, 0.0
+        # Track sets larger than the device: batch k+1 is packed on the host and uploaded on a second stream while batch
+        # k is being integrated (srb_integrate never synchronises; the reference's loop at calc.py:257-267 is serial)
+        upload = torch.cuda.Stream(self.device) if len(batches) > 1 else None
+        timers = []
         try:
             for b in batches:
                 if isinstance(b, tuple):
@@ -250,11 +262,13 @@ class SynchRad(Utilities):
                     t_pack += time.perf_counter() - t0
                 res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
                                        spectra=None if res is None else res.spectra,
-                                       counters_into=None if res is None else res.counters, **run)
+                                       counters_into=None if res is None else res.counters, upload_stream=upload, **run)
+                timers.append(res.events)
                 h2d += int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes
                            + packed.itStart.nbytes + packed.itEnd.nbytes + packed.itSnaps.nbytes)
                 upd += int(packed.updates_per_node)
-                ms += res.elapsed_ms
+            torch.cuda.synchronize(self.device)
+            ms = float(sum(e0.elapsed_time(e1) for e0, e1 in timers))
         finally:
             if track_source is not None:
                 track_source.close()

@@ -56,7 +56,7 @@ class DeviceGrid:
 
 
 class Result:
-    __slots__ = ('spectra', 'counters', 'info', 'updates', 'elapsed_ms', '_keep', '_kind_dev')
+    __slots__ = ('spectra', 'counters', 'info', 'updates', 'elapsed_ms', 'events', '_keep', '_kind_dev')
 
     @property
     def kind(self):
@@ -68,7 +68,7 @@ class Result:
 
 def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='auto',
               counters=True, device_tracks=None, timing=False, timeStep=None,
-              max_scratch_bytes=None, spectra=None, counters_into=None):
+              max_scratch_bytes=None, spectra=None, counters_into=None, upload_stream=None):
     """Run the hot path for the packed tracks of this rank.
 
     Returns Result with `spectra`: list of float64 device tensors (nSnaps, nPhi, nAxis2, nOmega).
@@ -76,6 +76,9 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
     how track sets larger than the device memory are processed batch by batch.
     `device_tracks` (optional) are tracks already resident on the device: a dict with the
     PackedTracks field names holding torch tensors (used by bench.py's device-resident leg).
+    `timing`: True -> elapsed_ms is filled (synchronises); 'events' -> only the CUDA events are recorded (`events`), the
+    caller reads them after its own synchronisation.  `upload_stream`: stream for the H2D copies of `packed` (the compute
+    stream waits for them), so that they overlap the kernel of a previous call.
     """
     lib = _lib.load()
     dev = grid.device
@@ -90,12 +93,17 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
         if device_tracks is None:
             d = {}
             names = ('x', 'y', 'z', 'ux', 'uy', 'uz')
-            for nm, a in zip(names, packed.coords):
-                d[nm] = torch.from_numpy(a.view(a.dtype)).to(dev, non_blocking=True)
-            d['offsets'] = torch.from_numpy(packed.offsets.view(np.int64)).to(dev, non_blocking=True)
-            d['w'] = torch.from_numpy(packed.w).to(dev, non_blocking=True)
-            for nm in ('itStart', 'itEnd', 'itSnaps'):
-                d[nm] = torch.from_numpy(getattr(packed, nm).view(np.int32)).to(dev, non_blocking=True)
+            with torch.cuda.stream(upload_stream if upload_stream is not None else stream):
+                for nm, a in zip(names, packed.coords):
+                    d[nm] = torch.from_numpy(a.view(a.dtype)).to(dev, non_blocking=True)
+                d['offsets'] = torch.from_numpy(packed.offsets.view(np.int64)).to(dev, non_blocking=True)
+                d['w'] = torch.from_numpy(packed.w).to(dev, non_blocking=True)
+                for nm in ('itStart', 'itEnd', 'itSnaps'):
+                    d[nm] = torch.from_numpy(getattr(packed, nm).view(np.int32)).to(dev, non_blocking=True)
+            if upload_stream is not None:
+                stream.wait_stream(upload_stream)
+                for v in d.values():
+                    v.record_stream(stream)            # allocated on the upload stream, consumed on the compute stream
             n_tracks, total, stride = packed.n, packed.total, packed.snapStride
         else:
             d = device_tracks
@@ -163,11 +171,13 @@ def integrate(Args, dtype, grid, packed, comp, nSnaps, native=False, phasor='aut
         torch.cuda.nvtx.range_pop()
         _lib.check(rc)
         res = Result()
-        res.elapsed_ms = None
+        res.elapsed_ms, res.events = None, None
         if timing:
             e1.record(stream)
-            e1.synchronize()
-            res.elapsed_ms = e0.elapsed_time(e1)
+            res.events = (e0, e1)
+            if timing != 'events':
+                e1.synchronize()
+                res.elapsed_ms = e0.elapsed_time(e1)
         info = _lib.srb_launch_info()
         lib.srb_last_launch(ctypes.byref(info))
         res._kind_dev = cnt[2:3].clone() if cnt is not None else None

@@ -173,11 +173,32 @@ def snap_iterations(it_range, nSnaps):
         np.linspace(it_range[0], it_range[1], int(nSnaps) + 1, dtype=np.uint32)[1:])
 
 
-def select_tracks(n_available, Np_max, rank, size):
-    """Indices of the tracks this rank integrates: the first min(Np_max, N) tracks,
-    round-robin over ranks (calc.py:204-212, 230-236)."""
+def select_tracks(n_available, Np_max, rank, size, lengths=None, partition='round_robin'):
+    """Indices of the tracks this rank integrates, out of the first min(Np_max, N) tracks.
+
+    'round_robin' (default): tracks[rank::size], the reference's split (calc.py:204-212, 230-236).
+    'balanced' (extension): contiguous slices with equal work sum(n_p - 1) per rank, for track sets whose
+    lengths vary a lot (needs `lengths`, the sample counts of those tracks).  The spectrum is a sum over particles, so
+    the partition changes the result only through the summation order; rank-local weight normalisation (Q7) follows
+    the partition, as it follows the reference's."""
     n = n_available if Np_max is None else min(int(Np_max), n_available)
-    return np.arange(n)[rank::size]
+    if partition == 'round_robin' or size == 1:
+        return np.arange(n)[rank::size]
+    if partition != 'balanced':
+        raise ValueError(f"partition must be 'round_robin' or 'balanced', got {partition!r}")
+    work = np.maximum(np.asarray(lengths[:n], dtype=np.int64) - 1, 0)
+    csum = np.concatenate(([0], np.cumsum(work)))
+    total = int(csum[-1])
+    # slice boundaries at the track starts nearest to the ideal cut points r * total / size
+    bounds = [0]
+    for r in range(1, size):
+        target = (total * r) / size
+        i = int(np.searchsorted(csum, target, side='left'))
+        if i > 0 and abs(csum[i - 1] - target) <= abs(csum[min(i, n)] - target):
+            i -= 1
+        bounds.append(min(max(i, bounds[-1]), n))
+    bounds.append(n)
+    return np.arange(bounds[rank], bounds[rank + 1])
 
 
 def normalized_weights(weights, mode):

@@ -16,12 +16,16 @@ sys.path.insert(0, HERE)
 import cases  # noqa: E402
 
 
-def problem():
+def problem(balanced=False):
     tracks, dt = cases.c5_tracks_numpy(7, 600)
     for i, t in enumerate(tracks):
         t[6] = 1.0 + 0.25 * i
     tracks = [t[:7] + [s] for t, s in zip(tracks, (0, 3, 0, 7, 1, 0, 2))]
     args = cases.c5_args(grid=(256, 6, 4))
+    if balanced:        # extension Args['partition'] = 'balanced': tracks of very different lengths, contiguous slices
+        tracks = [[c[:n] for c in t[:6]] + t[6:] for t, n in zip(tracks, (600, 40, 90, 500, 30, 600, 75))]
+        args['partition'] = 'balanced'
+        return args, tracks, dt, dict(comp='cartesian', nSnaps=2, it_range=(0, 610))
     kw = dict(comp='cartesian', Np_max=6, weights_normalize='mean', nSnaps=2, it_range=(0, 610))
     return args, tracks, dt, kw
 
@@ -36,7 +40,7 @@ def main():
         torch.cuda.set_device(0)
         dist.init_process_group('gloo')
     from synchrad.calc import SynchRad
-    args, tracks, dt, kw = problem()
+    args, tracks, dt, kw = problem(balanced=len(sys.argv) > 2 and sys.argv[2] == 'balanced')
     args['ctx'] = 'mpi'
     calc = SynchRad(args)                       # NCCL group created here when none exists (one rank per GPU)
     assert calc.size == world and calc.rank == rank

@@ -113,3 +113,21 @@ def test_split_batches():
     assert host.split_batches([60, 60, 60], 100) == [(0, 1), (1, 2), (2, 3)]
     assert host.split_batches([30, 30, 30, 30, 500, 5, 5], 100) == [(0, 3), (3, 4), (4, 5), (5, 7)]
     assert host.split_batches([500], 100) == [(0, 1)]
+
+
+def test_balanced_partition_covers_every_track_once():
+    """Extension Args['partition']='balanced' (SURVEY §8e): contiguous slices of near-equal work sum(n_p - 1); the
+    default stays the reference's tracks[rank::size]."""
+    from synchrad_b200 import host
+    rs = np.random.RandomState(3)
+    for size in (1, 2, 3, 8):
+        lengths = rs.randint(2, 5000, size=57).tolist()
+        parts = [host.select_tracks(len(lengths), 50, r, size, lengths, 'balanced') for r in range(size)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(50))          # Np_max respected, no overlap
+        assert all(np.all(np.diff(p) == 1) for p in parts if len(p) > 1)          # contiguous
+        work = [sum(lengths[i] - 1 for i in p) for p in parts]
+        rr = [sum(lengths[i] - 1 for i in host.select_tracks(len(lengths), 50, r, size)) for r in range(size)]
+        assert max(work) <= max(rr) + max(lengths)            # never much worse than round robin, exact cover above
+    np.testing.assert_array_equal(host.select_tracks(10, 7, 1, 3), [1, 4])       # reference split unchanged
+    with pytest.raises(ValueError):
+        host.select_tracks(5, None, 0, 2, [3] * 5, 'nope')
