@@ -107,49 +107,112 @@ SRB_HD void lit_prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   }
 }
 
-// main phase, lane = interleaved tile {lane + 32k}: the reference's per-node loop body
+// sin/cos of an fp32 phase (the value the reference feeds to sin()/cos()): range reduction to [-pi, pi], then the SFU
+// approximations (abs error 2^-21.4 = 4e-7 on that range).  |x| < 48000: three-term Cody-Waite reduction in fp32
+// (2*pi = 6.28125 + 1.9350052e-3 + 3.0199e-7, q*C exact for the first two; error 1.2e-7); larger arguments (the near
+// field's 1e10 rad phases) are reduced exactly on the FP64 pipe.  2 MUFU + 7 FP32 ops against ~25 for sincosf(), no
+// conversions on the common path.  The error is far below the fp32 phase noise the mode reproduces (|phase| * 6e-8)
+// and the 1e-4 tolerance; measured against the reference's fp32 vectors: see tests.
+template <bool BIG>
+SRB_HD void lit_sincos(float x, float* sn, float* cs) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  if (!BIG) {
+    const float q = __fadd_rn(fmaf(x, 0.15915494309189535f, 12582912.0f), -12582912.0f);
+    r = fmaf(q, -6.28125f, x);
+    r = fmaf(q, -1.9350051879882812e-3f, r);
+    r = fmaf(q, -3.019916050561733e-7f, r);
+  } else {
+    const double xd = (double)x;
+    const double t = fma(xd, 0.15915494309189535, 6755399441055744.0);
+    const double qd = t - 6755399441055744.0;
+    r = (float)fma(qd, -6.283185307179586, xd);
+  }
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+#else
+  *sn = sinf(x); *cs = cosf(x);
+#endif
+}
+
+// the accumulation of one step for the lane's TW nodes: one straight-line block (eight independent sincos/accumulate
+// chains per lane); BIG: some phase of the warp is beyond the fp32 Cody-Waite range
+template <class C, bool BIG>
+SRB_HD void lit_accumulate(const float* R, const float* ph, uint32_t pass, bool useFF, ThreadState<C>& st) {
+  constexpr int TW = C::TW;
+#pragma unroll
+  for (int k = 0; k < TW; k++) {
+    float sn, cs;
+    lit_sincos<BIG>(ph[k], &sn, &cs);
+    const bool on = (pass >> k) & 1u;
+    sn = on ? sn : 0.0f; cs = on ? cs : 0.0f;              // a failed node adds exactly 0 (amplitudes are finite)
+    if (C::MODE == MODE_FAR) {
+      if (useFF) { sn = fm(sn, st.ff[k]); cs = fm(cs, st.ff[k]); }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        st.acc[k * 6 + c] = fmaf(R[c], cs, st.acc[k * 6 + c]);
+        st.acc[k * 6 + 3 + c] = fmaf(R[c], sn, st.acc[k * 6 + 3 + c]);
+      }
+    } else {
+      const float wr = fm(st.wl[k], R[7]);
+      const float ws = fm(wr, sn), wc = fm(wr, cs);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        st.acc[k * 6 + c] = fmaf(R[3 + c], cs, fmaf(-R[c], ws, st.acc[k * 6 + c]));
+        st.acc[k * 6 + 3 + c] = fmaf(R[3 + c], sn, fmaf(R[c], wc, st.acc[k * 6 + 3 + c]));
+      }
+    }
+  }
+}
+
+// main phase, lane = interleaved tile {lane + 32k}: the reference's per-node loop body.  What is kept literally is
+// everything that shapes the result at the 1e-4 level: tracks, tables, tau, the amplitude and the PHASE in fp32
+// (rounded product, kernel_farfield.cl:65-67) and the per-node Nyquist guard on those phases (:68-72).  The
+// accumulation uses fused multiply-adds (OpenCL leaves the contraction of `Re += A*cos` to the driver, Q8) and
+// sin/cos of the fp32 phase come from the SFU (lit_sincos) instead of libm.
 template <class C>
 SRB_HD void lit_main_phase(const Params& P, const Geom& g, const WarpSmem<C>& sm, int cnt, int lane,
                            ThreadState<C>& st) {
   constexpr int TW = C::TW;
   const bool useFF = (C::MODE == MODE_FAR && P.comp == COMP_CART_CPLX && P.formFactor != nullptr);
   const float PI_F = (float)3.14159265358979323846;
+  // the lane's nodes are j = cLo + lane + 32k: its first nValid = ceil((n - lane) / 32) of them exist
+  const int nNodes = (int)(g.cHi - g.cLo);
+  int nValid = lane < nNodes ? (nNodes - 1 - lane) / 32 + 1 : 0;
+  nValid = nValid < TW ? nValid : TW;
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(nValid));      // (keeps ptxas from re-deriving it from eight predicates inside the loop)
+#endif
+  uint32_t nPass = 0;
   for (int s = 0; s < cnt; s++) {
     float R[8];
 #pragma unroll
     for (int k = 0; k < C::NREC; k++) R[k] = sm.rec[s][k];
+    // the guard of the lane's nodes first (branch-free), then one straight-line block for all of them: eight
+    // independent sincos/accumulate chains per lane instead of eight basic blocks executed one after the other
+    float ph[TW];
+    uint32_t pass = 0u;
+    bool big = false;
 #pragma unroll
     for (int k = 0; k < TW; k++) {
-      if (g.cLo + (uint32_t)(lane + 32 * k) >= g.cHi) continue;
-      const float w = st.wl[k];
-      const float phase = fm(w, C::MODE == MODE_FAR ? R[3] : R[6]);
-      const float dPhase = fabsf(fs(phase, st.pprev[k]));
-      st.pprev[k] = phase;
-      st.nAll++;
-      if (dPhase < PI_F) {
-        st.nPass++;
-        float sn, cs;
-        sincos_t(phase, &sn, &cs);
-        if (C::MODE == MODE_FAR) {
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            float re = fm(R[c], cs), im = fm(R[c], sn);
-            if (useFF) { re = fm(re, st.ff[k]); im = fm(im, st.ff[k]); }
-            st.acc[k * 6 + c] = fa(st.acc[k * 6 + c], re);
-            st.acc[k * 6 + 3 + c] = fa(st.acc[k * 6 + 3 + c], im);
-          }
-        } else {
-          const float wr = fm(w, R[7]);
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const float c1 = fm(wr, R[c]), c2 = R[3 + c];
-            st.acc[k * 6 + c] = fa(st.acc[k * 6 + c], fa(fm(-c1, sn), fm(c2, cs)));
-            st.acc[k * 6 + 3 + c] = fa(st.acc[k * 6 + 3 + c], fa(fm(c1, cs), fm(c2, sn)));
-          }
-        }
-      }
+      ph[k] = fm(st.wl[k], C::MODE == MODE_FAR ? R[3] : R[6]);
+      const float dPhase = fabsf(fs(ph[k], st.pprev[k]));
+      st.pprev[k] = ph[k];
+      pass |= (k < nValid && dPhase < PI_F) ? (1u << k) : 0u;
+      big = big || !(fabsf(ph[k]) < 48000.0f);
     }
+    nPass += (uint32_t)__builtin_popcount(pass);
+#if defined(__CUDA_ARCH__)
+    if (!__any_sync(0xffffffffu, pass != 0u)) continue;      // (guard-dominated inputs: whole steps fail)
+    big = __any_sync(0xffffffffu, big);
+#else
+    if (!pass) continue;
+#endif
+    if (big) lit_accumulate<C, true>(R, ph, pass, useFF, st);
+    else lit_accumulate<C, false>(R, ph, pass, useFF, st);
   }
+  st.nPass += nPass;
+  st.nAll += (unsigned long long)(nValid * cnt);
 }
 
 template <class C>

@@ -149,9 +149,10 @@ def test_device_sincos_accuracy():
 
 @pytest.mark.parametrize('near', [False, True])
 def test_literal_fp32_mode_matches_the_fp32_oracle(oracle, near):
-    """float_mode='literal' (srb_literal.cuh): every operation in fp32 in the reference's order, per-node
-    guard on fp32 phases.  Agreement with the strict fp32 restatement, including IDENTICAL guard
-    decisions (in the near field fp32 phases of 1e10 rad make the guard fail at random)."""
+    """float_mode='literal' (srb_literal.cuh): tracks, tables, tau, amplitude and phase in fp32 in the reference's
+    order, per-node guard on the fp32 phases; accumulation with fused multiply-adds.  Agreement with the strict fp32
+    restatement to a few 1e-6 (north star: 1e-4), with IDENTICAL guard decisions (in the near field fp32 phases of
+    1e10 rad make the guard fail at random)."""
     tr, dt, info = cases.undulator_tracks(2, seed=3)
     kw = dict(L_screen=1e5) if near else {}
     comps = ['total', 'cartesian_complex'] if near else ['total', 'cartesian', 'cartesian_complex', 'spheric_complex']
@@ -163,7 +164,7 @@ def test_literal_fp32_mode_matches_the_fp32_oracle(oracle, near):
         rad, cnt = emu.run(a, tr, dt, comp=comp, sigma_particle=2e-5, nSnaps=2, nPC=2, **kw)
         assert cnt[0] == lit['passed'], (comp, cnt, lit['passed'])
         for k in rad:
-            assert max(rel_errors(rad[k], lit['radiation'][k])) < 1e-6, (comp, k)
+            assert max(rel_errors(rad[k], lit['radiation'][k])) < 5e-6, (comp, k, rel_errors(rad[k], lit['radiation'][k]))
 
 
 @pytest.mark.parametrize('grid', [(256, 3, 2), (200, 2, 3), (33, 2, 2), (600, 2, 2)])
