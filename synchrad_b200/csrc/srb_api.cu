@@ -95,8 +95,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 template <class C, int NU, int NP, int NS>
 struct alignas(128) WsSmem {
   srb::WsStage<C> stage[NU][NS];
-  double in[NU][NP][srb::WS_IN][srb::WS_NIN];        // TMA-staged input records of a producer's next sub-batch
-  uint64_t full[NU][NS], empty[NU][NS], inbar[NU][NP], xfer[NU][NS];
+  double in[NU][NP][2][srb::WS_IN][srb::WS_NIN];     // TMA-staged input records of a producer's next (pair of) sub-batches
+  uint64_t full[NU][NS], empty[NU][NS], inbar[NU][NP][2], xfer[NU][NS];
 };
 
 // NCW consumer warps per unit.  With two, the sub-batches alternate between them (a split of the GEMM's K dimension:
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
   if (threadIdx.x == 0) {
     for (int u = 0; u < NU; u++) {
       for (int i = 0; i < NS; i++) { mbar_init(&S.full[u][i], 32); mbar_init(&S.empty[u][i], 32); mbar_init(&S.xfer[u][i], 32); }
-      for (int q = 0; q < NP; q++) mbar_init(&S.inbar[u][q], 1);
+      for (int q = 0; q < NP; q++) { mbar_init(&S.inbar[u][q][0], 1); mbar_init(&S.inbar[u][q][1], 1); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -209,20 +209,30 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
     return;
   }
 
-  // ---- producer pidx of unit u: items k with k % NP == pidx
+  // ---- producer pidx of unit u.
+  // PAIRS (NS == 2 * NP): a producer owns the ring slots 2m, 2m + 1 with m % NP == pidx -- always the same two stages --
+  // and prepares the two sub-batches TOGETHER: the scalar chains of a step (two sincos, powers, the tile recurrence)
+  // are long and share the FP64 pipe with the DMMA stream (~26 cycles per dependent op under that load, against 9
+  // alone: tools/ws_pipe_mix.cu); two independent sub-batches in one instruction stream double the instruction-level
+  // parallelism of the warp.  Otherwise slot k belongs to producer k % NP.
+#ifndef SRB_WS_PAIRS
+#define SRB_WS_PAIRS 0     // measured: 2.69e12 with pairs against 2.93e12 without (the ring loses depth), profiles/r02_ws_tuning.md
+#endif
+  constexpr bool PAIRS = SRB_WS_PAIRS && NS == 2 * NP;
   struct Own { uint32_t kind, base, k, itStart; int cnt; uint64_t idx; bool valid; };   // idx: element of step `base` in the arrays
   bool flush2 = false;               // two consumer warps: a flush takes two consecutive ring slots (see above)
+  auto mine = [&](uint32_t kk) -> bool { return (PAIRS ? (kk >> 1) : kk) % (uint32_t)NP == (uint32_t)pidx; };
   auto next_own = [&](Own& o) {
     for (;;) {
       if (flush2) {
         flush2 = false;
         const uint32_t kk = k++;
-        if (kk % (uint32_t)NP == (uint32_t)pidx) { o.kind = 1u; o.base = 0u; o.cnt = 0; o.k = kk; o.idx = 0; o.valid = true; return; }
+        if (mine(kk)) { o.kind = 1u; o.base = 0u; o.cnt = 0; o.k = kk; o.idx = 0; o.valid = true; return; }
       }
       if (!w.next(P, it)) { o.valid = false; return; }
       const uint32_t kk = k++;
       if (it.kind == 1u && NCW > 1) flush2 = true;
-      if (kk % (uint32_t)NP == (uint32_t)pidx) {
+      if (mine(kk)) {
         o.kind = it.kind; o.base = it.base; o.cnt = it.cnt; o.k = kk; o.itStart = w.tv.itStart;
         o.idx = (uint64_t)((const double*)w.tv.x - (const double*)P.x) + it.base;
         o.valid = true;
@@ -230,83 +240,108 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
       }
     }
   };
+  auto next_pair = [&](Own& a, Own& b) {          // b: the odd slot of a's pair, if there is one
+    next_own(a);
+    b.valid = false;
+    if (PAIRS && a.valid && (a.k & 1u) == 0u) next_own(b);
+  };
   const uint64_t totalSteps = P.offsets[P.nTracks];
   // Staged inputs of the sub-batch whose first step is element idx: the 34 packed records (k_prepass: x, y, z, a, b per
   // step, 72 bytes) from the even index at or below idx - 1 (previous step + 16-byte alignment), ONE bulk copy.
   // Sub-batches at the edges of the arrays use plain loads.
   auto can_tma = [&](const Own& o) -> bool { return P.tmaOK && o.idx >= 2 && o.idx + 33 <= totalSteps; };
-  auto issue = [&](const Own& o) {
-    __syncwarp();                       // every lane has consumed the previous sub-batch's inputs
-    if (lane == 0 && can_tma(o)) {
-      uint64_t* bar = &S.inbar[u][pidx];
+  auto issue = [&](const Own& o, int slot) {
+    if (lane == 0 && o.valid && o.kind == 0u && can_tma(o)) {
+      uint64_t* bar = &S.inbar[u][pidx][slot];
       const uint64_t e0 = (o.idx - 1) & ~(uint64_t)1;
       mbar_arrive_expect_tx(bar, (uint32_t)(WS_NIN * WS_IN * 8));
-      tma_load_1d(&S.in[u][pidx][0][0], P.pre + e0 * WS_NIN, (uint32_t)(WS_NIN * WS_IN * 8), bar);
+      tma_load_1d(&S.in[u][pidx][slot][0][0], P.pre + e0 * WS_NIN, (uint32_t)(WS_NIN * WS_IN * 8), bar);
     }
   };
   WsConst kc;
   ws_const<C>(P, g, kc);
   unsigned long long nPass = 0, nAll = 0;
-  Own cur, nxt;
-  uint32_t inphase = 0u;
-  next_own(cur);
-  if (cur.valid && cur.kind == 0) issue(cur);
-  while (cur.valid) {
-    next_own(nxt);
-    const int sgi = (int)(cur.k % (uint32_t)NS);
-    mbar_wait(&S.empty[u][sgi], ((cur.k / (uint32_t)NS) & 1u) ^ 1u);
-    WsStage<C>& sg = S.stage[u][sgi];
-#if defined(SRB_WS_FAKE_PRODUCER)      // tuning aid: stages are filled once, then only handed over (consumer-only timing)
-    if (cur.kind == 0 && cur.k >= (uint32_t)(2 * NS * NP)) { mbar_arrive(&S.full[u][sgi]); cur = nxt; continue; }
-#endif
-    if (cur.kind == 0) {
-      const uint32_t itl = cur.base + (uint32_t)lane;
-      const bool active = lane < cur.cnt;
-      double x, y, z, a[3], b[3], xp = 0, yp = 0, zp = 0;
-      if (can_tma(cur)) {
-        mbar_wait(&S.inbar[u][pidx], inphase);
-        inphase ^= 1u;
-        const double (*in)[WS_NIN] = S.in[u][pidx];
-        const int sl = (int)(cur.idx - ((cur.idx - 1) & ~(uint64_t)1)) + lane;      // 1 or 2, + lane
-        x = in[sl][0]; y = in[sl][1]; z = in[sl][2];
+  uint32_t inphase = 0u;              // bit `slot`: phase of that input buffer's barrier
+  // inputs of sub-batch o (staged in `slot` or, at the edges of the arrays, plain loads) -> guard + amplitude
+  auto guard = [&](const Own& o, int slot, WsStep& ws) {
+    const uint32_t itl = o.base + (uint32_t)lane;
+    const bool active = lane < o.cnt;
+    double x, y, z, a[3], b[3], xp = 0, yp = 0, zp = 0;
+    if (can_tma(o)) {
+      mbar_wait(&S.inbar[u][pidx][slot], (inphase >> slot) & 1u);
+      inphase ^= 1u << slot;
+      const double (*in)[WS_NIN] = S.in[u][pidx][slot];
+      const int sl = (int)(o.idx - ((o.idx - 1) & ~(uint64_t)1)) + lane;      // 1 or 2, + lane
+      x = in[sl][0]; y = in[sl][1]; z = in[sl][2];
 #pragma unroll
-        for (int c = 0; c < 3; c++) { a[c] = in[sl][3 + c]; b[c] = in[sl][6 + c]; }
-        if (lane == 0) { xp = in[sl - 1][0]; yp = in[sl - 1][1]; zp = in[sl - 1][2]; }
-      } else {                          // edge of the arrays: plain loads
-        x = y = z = 0.0;
+      for (int c = 0; c < 3; c++) { a[c] = in[sl][3 + c]; b[c] = in[sl][6 + c]; }
+      if (lane == 0) { xp = in[sl - 1][0]; yp = in[sl - 1][1]; zp = in[sl - 1][2]; }
+    } else {                          // edge of the arrays: plain loads
+      x = y = z = 0.0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) a[c] = b[c] = 0.0;
-        const uint64_t e = cur.idx + (uint64_t)lane;
-        if (active) {
-          const double* q = P.pre + e * WS_NIN;
-          x = q[0]; y = q[1]; z = q[2];
+      for (int c = 0; c < 3; c++) a[c] = b[c] = 0.0;
+      const uint64_t e = o.idx + (uint64_t)lane;
+      if (active) {
+        const double* q = P.pre + e * WS_NIN;
+        x = q[0]; y = q[1]; z = q[2];
 #pragma unroll
-          for (int c = 0; c < 3; c++) { a[c] = q[3 + c]; b[c] = q[6 + c]; }
-        }
-        if (lane == 0 && itl > 0) { const double* q = P.pre + (e - 1) * WS_NIN; xp = q[0]; yp = q[1]; zp = q[2]; }
+        for (int c = 0; c < 3; c++) { a[c] = q[3 + c]; b[c] = q[6 + c]; }
       }
-      // tau = t - n.r in the reference's operation order (kernel_farfield.cl:65-67); the previous step's tau from the
-      // neighbouring lane, lane 0 recomputes it (0 for it == 0: phasePrev starts at 0, Q1)
-      const double tau = ssub(smul((double)(cur.itStart + itl), P.dt), sdot3(x, y, z, g.nx, g.ny, g.nz));
-      double tauPrev = __shfl_up_sync(0xffffffffu, tau, 1);
-      if (lane == 0)
-        tauPrev = itl == 0 ? 0.0 : ssub(smul((double)(cur.itStart + itl - 1), P.dt), sdot3(xp, yp, zp, g.nx, g.ny, g.nz));
-      WsStep ws;
-      ws_prep_guard<C>(P, g, kc, active, tau, tauPrev, a, b, ws, nPass, nAll);
-      // Every staged input has been CONSUMED by now (tau, tauPrev, the amplitude), not merely requested: a shared-memory
-      // load still queued in the LSU could be overtaken by the TMA engine's write (seen as a ~1e-8 run-to-run wobble
-      // of the spectrum when the copy was issued right after the loads).  The single input buffer is free for this
-      // producer's next sub-batch, whose copies then have the phasor part of this item (~2/3 of it) to land.
-      if (nxt.valid && nxt.kind == 0) issue(nxt);
-      const uint32_t fl = ws_prep_store<C>(P, kc, ws, sg, lane);
-      const uint32_t fullMask = __ballot_sync(0xffffffffu, fl == 1u);
-      const uint32_t anyMask = __ballot_sync(0xffffffffu, fl != 0u);
-      if (lane == 0) { sg.cnt = (uint32_t)cur.cnt; sg.fullMask = fullMask; sg.anyMask = anyMask; }
-    } else if (nxt.valid && nxt.kind == 0) {
-      issue(nxt);                       // flush item: nothing to read, the buffer is free
+      if (lane == 0 && itl > 0) { const double* q = P.pre + (e - 1) * WS_NIN; xp = q[0]; yp = q[1]; zp = q[2]; }
     }
-    mbar_arrive(&S.full[u][sgi]);
-    cur = nxt;
+    // tau = t - n.r in the reference's operation order (kernel_farfield.cl:65-67); the previous step's tau from the
+    // neighbouring lane, lane 0 recomputes it (0 for it == 0: phasePrev starts at 0, Q1)
+    const double tau = ssub(smul((double)(o.itStart + itl), P.dt), sdot3(x, y, z, g.nx, g.ny, g.nz));
+    double tauPrev = __shfl_up_sync(0xffffffffu, tau, 1);
+    if (lane == 0)
+      tauPrev = itl == 0 ? 0.0 : ssub(smul((double)(o.itStart + itl - 1), P.dt), sdot3(xp, yp, zp, g.nx, g.ny, g.nz));
+    ws_prep_guard<C>(P, g, kc, active, tau, tauPrev, a, b, ws, nPass, nAll);
+  };
+  auto finish = [&](const Own& o, WsStage<C>& sg, uint32_t fl) {
+    const uint32_t fullMask = __ballot_sync(0xffffffffu, fl == 1u);
+    const uint32_t anyMask = __ballot_sync(0xffffffffu, fl != 0u);
+    if (lane == 0) { sg.cnt = (uint32_t)o.cnt; sg.fullMask = fullMask; sg.anyMask = anyMask; }
+  };
+  Own A, B, nA, nB;
+  next_pair(A, B);
+  issue(A, 0); issue(B, 1);
+  while (A.valid) {
+    next_pair(nA, nB);
+    const int sgA = (int)(A.k % (uint32_t)NS), sgB = (int)((A.k + 1u) % (uint32_t)NS);
+    mbar_wait(&S.empty[u][sgA], ((A.k / (uint32_t)NS) & 1u) ^ 1u);
+    if (B.valid) mbar_wait(&S.empty[u][sgB], ((B.k / (uint32_t)NS) & 1u) ^ 1u);
+#if defined(SRB_WS_FAKE_PRODUCER)      // tuning aid: stages are filled once, then only handed over (consumer-only timing)
+    if (A.k >= (uint32_t)(2 * NS * NP)) { mbar_arrive(&S.full[u][sgA]); if (B.valid) mbar_arrive(&S.full[u][sgB]); A = nA; B = nB; continue; }
+#endif
+    const bool subA = A.kind == 0u, subB = B.valid && B.kind == 0u;
+    WsStep wa, wb;
+    wa.flag = wb.flag = 0u;
+    if (subA) guard(A, 0, wa);
+    if (subB) guard(B, 1, wb);
+    // Every staged input has been CONSUMED by now (tau, tauPrev, the amplitude), not merely requested: a shared-memory
+    // load still queued in the LSU could be overtaken by the TMA engine's write (seen as a ~1e-8 run-to-run wobble
+    // of the spectrum when the copy was issued right after the loads).  The input buffers are free for this
+    // producer's next sub-batches, whose copies then have the phasor part of this item (~2/3 of it) to land.
+    __syncwarp();
+    issue(nA, 0); issue(nB, 1);
+    WsStage<C>& sa = S.stage[u][sgA];
+    WsStage<C>& sb = S.stage[u][sgB];
+    if (subA && subB && __all_sync(0xffffffffu, wa.flag == 1u && wb.flag == 1u)) {
+      // both sub-batches all-pass at every lane (the common case): ONE straight-line block for the two phasor chains
+      ws_seeds<C>(P, kc, wa.tau, wa.A, sa, lane);
+      ws_seeds<C>(P, kc, wb.tau, wb.A, sb, lane);
+      sa.rec[lane][0] = Dbl2{wa.A[0], wa.A[1]}; sa.rec[lane][1] = Dbl2{wa.A[2], wa.tau};
+      sb.rec[lane][0] = Dbl2{wb.A[0], wb.A[1]}; sb.rec[lane][1] = Dbl2{wb.A[2], wb.tau};
+      sa.rng[lane] = wa.lo | (wa.hi << 10) | (1u << 30);
+      sb.rng[lane] = wb.lo | (wb.hi << 10) | (1u << 30);
+      if (lane == 0) { sa.cnt = 32u; sa.fullMask = 0xffffffffu; sa.anyMask = 0xffffffffu; sb.cnt = 32u; sb.fullMask = 0xffffffffu; sb.anyMask = 0xffffffffu; }
+    } else {
+      if (subA) finish(A, sa, ws_prep_store<C>(P, kc, wa, sa, lane));
+      if (subB) finish(B, sb, ws_prep_store<C>(P, kc, wb, sb, lane));
+    }
+    mbar_arrive(&S.full[u][sgA]);
+    if (B.valid) mbar_arrive(&S.full[u][sgB]);
+    A = nA; B = nB;
   }
   if (P.counters && nAll) { atomicAdd(P.counters, nPass); atomicAdd(P.counters + 1, nAll); }
 }
