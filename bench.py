@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'particle*step*spectral-pt updates/s'
 ALG_SLOTS = {'double': 30.0, 'float': 30.0, 'native': 9.0}   # algorithmic issue slots per update
 GRID = (256, 32, 32)
-KIND_NAMES = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair, DFMA'}
+KIND_NAMES = {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair, DFMA', 5: 'corrected recurrence'}
 
 
 def kernel_label(info, fp64, kind=None):

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('SYNCHRAD_B200_LIB') or os.path.join(_HERE, 'csrc', 'l
 MODE = {'far': 0, 'near': 1}
 COMP = {'total': 0, 'cartesian': 1, 'cartesian_complex': 2, 'spheric': 3, 'spheric_complex': 4}
 DTYPE = {'double': 0, 'float': 1, 'float_literal': 2}
-PHASOR = {'auto': 0, 'direct': 1, 'recur': 2, 'pair': 3, 'pair_fma': 4}
+PHASOR = {'auto': 0, 'direct': 1, 'recur': 2, 'pair': 3, 'pair_fma': 4, 'drec': 5}
 
 # every symbol include/synchrad_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ('srb_version', 'srb_last_error', 'srb_num_spectra', 'srb_scratch_bytes',

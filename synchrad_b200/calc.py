@@ -291,7 +291,7 @@ class SynchRad(Utilities):
         self.last_run = {
             'passed_updates': int(c[0]), 'visited_updates': int(c[1]),
             'updates': upd * int(self.Args['numGridNodes']), 'batches': len(batches),
-            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair_fma'}[res.kind], 'integrate_ms': ms,
+            'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair_fma', 5: 'drec'}[res.kind], 'integrate_ms': ms,
             'tile_width': int(res.info.tile_width), 'particle_chunks': int(res.info.n_particle_chunks),
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
             'h2d_bytes': h2d,

@@ -48,6 +48,7 @@ constexpr int NW = SRB_NW;   // warps (= virtual directions) per block
 // resident blocks per SM the register budget is tuned for: accumulators must stay in registers
 template <class C> constexpr int min_blocks() {
   constexpr int accRegs = C::NACC * (int)sizeof(typename C::TM) / 4;
+  if (C::KIND == srb::KIND_DREC) return C::NACC <= 24 ? 3 : 2;       // 17 KB of seeds per warp; 48-96 accumulator registers
   if (C::KIND == srb::KIND_DIRECT || C::KIND == srb::KIND_LITERAL) return accRegs <= 48 ? 4 : SRB_MINB_DIRECT;   // fp32 direct: 48 accumulator registers
   if (C::MMA) return C::NACC > 48 ? 2 : SRB_MINB_MMA;   // 16-node tiles: 64 fp64 accumulators per lane
   if (C::PAIR && sizeof(typename C::TM) == 8) return SRB_MINB > 3 ? 3 : SRB_MINB;   // measured: 168 regs beat 128
@@ -546,7 +547,7 @@ bool pick_ws(int tw, int nc, Launcher* L) {
   return false;
 }
 
-using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::KIND_PAIR_FMA; using srb::MODE_FAR; using srb::MODE_NEAR;
+using srb::KIND_DREC; using srb::Cfg; using srb::KIND_DIRECT; using srb::KIND_RECUR; using srb::KIND_LITERAL; using srb::KIND_PAIR; using srb::KIND_PAIR_FMA; using srb::MODE_FAR; using srb::MODE_NEAR;
 
 // kind, mode, dtype, native, tile width, far components -> kernel
 bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* L) {
@@ -562,6 +563,9 @@ bool pick(int kind, int mode, int dtype, bool native, int tw, int nc, Launcher* 
   // direct
   SRB_BOTH(KIND_DIRECT, MODE_FAR, false, 8, 3) SRB_BOTH(KIND_DIRECT, MODE_FAR, false, 4, 3) SRB_BOTH(KIND_DIRECT, MODE_FAR, false, 2, 3)
   SRB_BOTH(KIND_DIRECT, MODE_NEAR, false, 8, 3) SRB_BOTH(KIND_DIRECT, MODE_NEAR, false, 4, 3) SRB_BOTH(KIND_DIRECT, MODE_NEAR, false, 2, 3)
+  // direct layout, corrected recurrence: fp64, uniform grids, any phase magnitude (srb_drec.cuh)
+  SRB_CASE(KIND_DREC, MODE_FAR, 0, false, 8, 3, double) SRB_CASE(KIND_DREC, MODE_FAR, 0, false, 4, 3, double) SRB_CASE(KIND_DREC, MODE_FAR, 0, false, 2, 3, double)
+  SRB_CASE(KIND_DREC, MODE_NEAR, 0, false, 8, 3, double) SRB_CASE(KIND_DREC, MODE_NEAR, 0, false, 4, 3, double) SRB_CASE(KIND_DREC, MODE_NEAR, 0, false, 2, 3, double)
   // direct, fp32 native sincos
   SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 8, 3, float) SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 4, 3, float)
   SRB_CASE(KIND_DIRECT, MODE_FAR, 1, true, 2, 3, float)
@@ -628,11 +632,15 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   else if (g->phasor == SRB_PHASOR_RECUR || !pairOk || (preferRecur && g->phasor == SRB_PHASOR_AUTO)) p->kind = KIND_RECUR;
   else p->kind = KIND_PAIR;
   // near field: phase = omega*(t+R) ~ omega*L.  Beyond 2^18 rad the recurrence cannot track the
-  // reference's rounded phase to 1e-9 (srb_core.cuh, flag 3), every step would fall back, so the
-  // direct kernel (full lane layout) is chosen outright.
-  if (g->phasor == SRB_PHASOR_AUTO && g->mode == SRB_MODE_NEAR && g->dtype == SRB_DTYPE_F64 &&
+  // reference's rounded phase to 1e-9 (srb_core.cuh, flag 3), every step would fall back: the corrected-recurrence
+  // kernel (srb_drec.cuh: direct layout, per-update correction onto the rounded phase) takes over.
+  if (g->phasor == SRB_PHASOR_AUTO && g->mode == SRB_MODE_NEAR && g->dtype == SRB_DTYPE_F64 && uniform &&
       std::fabs(g->omega_last_host * g->L_screen) > 262144.0)
-    p->kind = KIND_DIRECT;
+    p->kind = KIND_DREC;
+  if (g->phasor == SRB_PHASOR_DREC) {
+    if (!uniform || g->dtype != SRB_DTYPE_F64) return fail("the corrected-recurrence kernel needs fp64 and an ascending uniform omega grid");
+    p->kind = KIND_DREC;
+  }
   if (g->dtype == SRB_DTYPE_F32_LITERAL) p->kind = KIND_LITERAL;
   p->native = (p->kind == KIND_DIRECT && g->dtype == SRB_DTYPE_F32 && g->native != 0);   // Q9
   const int tiles = p->kind == KIND_RECUR ? 16 : 32;
@@ -640,6 +648,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   int twMax, twMin;
   if (p->kind == KIND_RECUR) { twMax = g->mode == SRB_MODE_FAR ? 16 : 8; twMin = twMax / 4; }
   else if (p->kind == KIND_PAIR) { twMax = !spheric ? 16 : 8; twMin = 2; }
+  else if (p->kind == KIND_DREC) { twMax = 8; twMin = 2; }
   else { twMax = g->dtype == SRB_DTYPE_F64 ? 4 : 8; twMin = 2; }   // fp64 direct: 4 nodes/lane measured fastest
   p->tw = twMax;
   for (int tw = twMin; tw <= twMax; tw *= 2) if ((uint32_t)(tiles * tw) >= g->nOmega) { p->tw = tw; break; }

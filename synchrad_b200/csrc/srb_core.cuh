@@ -58,7 +58,10 @@ namespace srb {
 
 enum { MODE_FAR = 0, MODE_NEAR = 1 };
 enum { COMP_TOTAL = 0, COMP_CART = 1, COMP_CART_CPLX = 2, COMP_SPH = 3, COMP_SPH_CPLX = 4 };
-enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3, KIND_PAIR_FMA = 4 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh
+enum { KIND_DIRECT = 0, KIND_RECUR = 1, KIND_LITERAL = 2, KIND_PAIR = 3, KIND_PAIR_FMA = 4, KIND_DREC = 5 };   // LITERAL: srb_literal.cuh, PAIR: srb_pair.cuh
+// KIND_DREC (srb_drec.cuh): the direct kernel's layout with the per-node sincos replaced by a per-lane recurrence along
+// omega plus a per-update first-order correction onto the reference's ROUNDED phase -- phases of any magnitude (near
+// field at large L: 1e10 rad) on uniform grids, fp64.
 // (kind 5 was the experimental gridding / type-1 NUFFT kernel of round 1: correct but 0.75-0.81x the pair kernel after two
 //  iterations, profiles/r02_spread_v2_decision.txt; removed from the library, kept on the git branch `spread-kernel`)
 // KIND_PAIR_FMA: the pair kernel with its accumulation on the scalar FP64 pipe (DFMA) where KIND_PAIR uses DMMA
@@ -277,7 +280,7 @@ struct Cfg {
   // accumulators per node: split layout (recurrence) holds one part (cos or sin) of NV sums,
   // the direct layout holds Re and Im of the 3 (far: NC) amplitude components
   static constexpr int NPN = (KIND_ == KIND_RECUR) ? NV
-      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || PAIR)) ? 2 * NC_ : 6);
+      : ((MODE_ == MODE_FAR && (KIND_ == KIND_DIRECT || KIND_ == KIND_DREC || PAIR)) ? 2 * NC_ : 6);
   static constexpr int NACC = NPN * TW_;
   // rec row: V[NV], then (recurrence) 2cos(d), cos(d), sin(d) | (direct) tau (fp32: tau_hi, tau_lo) ; padded to even
   //          (pair) V[NC], tau (flag 3 only), pad to QOFF, then A_c*(cos,sin) of the TW/2 pair offsets for
@@ -295,12 +298,20 @@ struct Cfg {
   static constexpr int NREC_FLUSH = MMA ? (((32 * NACC - 16 - NSEED * 33 + 31) / 32 + 3) & ~3) : 0;
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
       : PAIR ? (NREC_PAIR > NREC_FLUSH ? NREC_PAIR : NREC_FLUSH)
+      : KIND_ == KIND_DREC ? ((NV + 5 + 1) & ~1)   // V[NV], tau, R^32 (Re, Im), conj-rotated... see srb_drec.cuh: tau, wr, wi, 2cos, pad
       : (((NV + (KIND_ == KIND_RECUR ? 3 : (sizeof(TM_) == 4 ? 2 : 1))) + 1) & ~1);   // direct, fp32: tau as hi + lo
-  using TW_T = typename std::conditional<KIND_ == KIND_DIRECT, double, TM_>::type;      // type of the lane's omega nodes
+  static constexpr bool DIRECTLIKE = KIND_ == KIND_DIRECT || KIND_ == KIND_DREC;         // lane = tile {lane + 32k}, Re and Im per node
+  using TW_T = typename std::conditional<DIRECTLIKE, double, TM_>::type;                 // type of the lane's omega nodes
 };
 
+// KIND_DREC: per step the two-level phasor seeds of the 32 lanes' first nodes m = 8a + b: Z_b = E R^b (b = 0..7) and
+// Y_a = R^(8a) (a = 0..3), S_m = Y_a Z_b; rows padded to 13 pairs (lane = step 128-bit stores conflict free)
+struct alignas(16) Cpx { double re, im; };
+template <bool ON> struct DrecSmem {};
+template <> struct alignas(16) DrecSmem<true> { Cpx seed[SUB][13]; };
+
 template <class C>
-struct WarpSmem {
+struct WarpSmem : DrecSmem<C::KIND == KIND_DREC> {
   typename C::TM rec[SUB][C::NREC];       // per-step record (see Cfg::NREC)
   uint32_t rng[SUB];                      // lo | hi<<10 | flag<<30 (chunk-relative pass range)
   typename C::TM seeds[C::NSEED][SUB + 1];  // [part*16+tile][step]: cos|sin of the tile's first node
@@ -309,7 +320,8 @@ struct WarpSmem {
 template <class C>
 struct ThreadState {
   typename C::TM acc[C::NACC];
-  typename C::TW_T wl[(C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) ? C::TW : 1];   // this lane's omega nodes
+  typename C::TW_T wl[(C::DIRECTLIKE || C::KIND == KIND_LITERAL) ? C::TW : 1];   // this lane's omega nodes
+  double eps[C::KIND == KIND_DREC ? C::TW : 1];   // KIND_DREC: table node minus ideal uniform-grid node (double-double residue)
   typename C::TM pprev[C::KIND == KIND_LITERAL ? C::TW : 1];   // literal kind: per-node phasePrev
   typename C::TM ff[C::KIND == KIND_LITERAL ? C::TW : 1];      // literal kind: per-node FormFactor
   unsigned long long nPass, nAll;
@@ -364,6 +376,10 @@ template <class C> SRB_HD void pair_mma_load_frag(const WarpSmem<C>&, int, Threa
 template <class C> SRB_HD void pair_mma_load_tile(const WarpSmem<C>&, int, ThreadState<C>&);
 template <class C> SRB_HD void pair_mma_store_tile(WarpSmem<C>&, int, const ThreadState<C>&);
 template <class C> SRB_HD void pair_node_amp(const ThreadState<C>&, int, double*, double*);
+// corrected-recurrence kind (srb_drec.cuh)
+template <class C> SRB_HD void drec_init_lane(const Params&, const Geom&, int, ThreadState<C>&);
+template <class C> SRB_HD void make_seeds_drec(const Params&, const Geom&, double, WarpSmem<C>&, int, double*);
+template <class C> SRB_HD void main_drec(const Params&, const Geom&, const WarpSmem<C>&, int, uint32_t, uint32_t, int, ThreadState<C>&);
 // literal fp32 kind (srb_literal.cuh), used by warp_task below
 template <class C> SRB_HD void lit_prep_phase(const Params&, const Geom&, const TrackView&, uint32_t, int, int, WarpSmem<C>&);
 template <class C> SRB_HD void lit_main_phase(const Params&, const Geom&, const WarpSmem<C>&, int, int, ThreadState<C>&);
@@ -550,6 +566,11 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
     const double wl = (double)((const typename C::TI*)P.omega)[P.descending ? g.cLo : g.cHi - 1];
     const bool big = sizeof(TM) == 8 && fabs(wl * tau) > 262144.0;
     if (big) flag = 3u; else make_seeds<C>(P, g, tau, sm, lane, last);
+  }
+  if constexpr (C::KIND == KIND_DREC) {
+    double w4[4];
+    make_seeds_drec<C>(P, g, tau, sm, lane, w4);
+    sm.rec[lane][C::NV + 1] = w4[0]; sm.rec[lane][C::NV + 2] = w4[1]; sm.rec[lane][C::NV + 3] = w4[2]; sm.rec[lane][C::NV + 4] = w4[3];
   }
   sm.rng[lane] = lo | (hi << 10) | (flag << 30);
   st.nPass += hi - lo;
@@ -764,7 +785,7 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
     double re[3], im[3];
     if constexpr (C::PAIR) {
       pair_node_amp<C>(me, k, re, im);
-    } else if constexpr (C::KIND == KIND_DIRECT) {
+    } else if constexpr (C::DIRECTLIKE) {
 #pragma unroll
       for (int c = 0; c < NCF; c++) { re[c] = (double)me.acc[k * NPN + c]; im[c] = (double)me.acc[k * NPN + NCF + c]; }
     } else {
@@ -899,7 +920,8 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
   }
   SRB_LANES_BEGIN
     SRB_ST.nPass = 0; SRB_ST.nAll = 0;
-    if (C::KIND == KIND_DIRECT || C::KIND == KIND_LITERAL) {
+    if constexpr (C::KIND == KIND_DREC) drec_init_lane<C>(P, g, lane, SRB_ST);
+    if (C::DIRECTLIKE || C::KIND == KIND_LITERAL) {
 #pragma unroll
       for (int k = 0; k < C::TW; k++) {
         const uint32_t j = g.cLo + (uint32_t)(lane + 32 * k);
@@ -983,6 +1005,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
 #endif
           }
           else if constexpr (C::PAIR) main_pair<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
+          else if constexpr (C::KIND == KIND_DREC) main_drec<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
           else main_direct<C>(P, g, sm, cnt, fullMask, anyMask, lane, SRB_ST);
         SRB_LANES_END
         }

@@ -15,6 +15,7 @@
 #pragma once
 #include "srb_core.cuh"
 #include "srb_pair.cuh"
+#include "srb_drec.cuh"
 
 namespace srb {
 

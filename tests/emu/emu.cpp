@@ -116,6 +116,9 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   EMU_CASE(KIND_RECUR, MODE_NEAR, 8) EMU_CASE(KIND_RECUR, MODE_NEAR, 4) EMU_CASE(KIND_RECUR, MODE_NEAR, 2)
   EMU_CASE(KIND_DIRECT, MODE_FAR, 8) EMU_CASE(KIND_DIRECT, MODE_FAR, 4) EMU_CASE(KIND_DIRECT, MODE_FAR, 2)
   EMU_CASE(KIND_DIRECT, MODE_NEAR, 8) EMU_CASE(KIND_DIRECT, MODE_NEAR, 4) EMU_CASE(KIND_DIRECT, MODE_NEAR, 2)
+#define EMU_DREC(M, TWV) if (kind == KIND_DREC && !f32 && g->mode == M && tw == TWV) { run_all<Cfg<double, double, M, KIND_DREC, TWV, false, 3>>(P, counters); ok = true; }
+  EMU_DREC(MODE_FAR, 8) EMU_DREC(MODE_FAR, 4) EMU_DREC(MODE_FAR, 2) EMU_DREC(MODE_NEAR, 8) EMU_DREC(MODE_NEAR, 4) EMU_DREC(MODE_NEAR, 2)
+#undef EMU_DREC
 #undef EMU_CASE
 #undef EMU_CASE1
 #define EMU_PAIR3(TWV) if (kind == KIND_PAIR && g->mode == MODE_FAR && tw == TWV && spheric) { if (f32) run_all<Cfg<double, float, MODE_FAR, KIND_PAIR, TWV, false, 3>>(P, counters); else run_all<Cfg<double, double, MODE_FAR, KIND_PAIR, TWV, false, 3>>(P, counters); ok = true; }

@@ -15,7 +15,8 @@ _SRC = [os.path.join(_HERE, 'emu.cpp'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_core.cuh'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_pair.cuh'),
         os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_literal.cuh'),
-        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_ws.cuh')]
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_ws.cuh'),
+        os.path.join(_HERE, '..', '..', 'synchrad_b200', 'csrc', 'srb_drec.cuh')]
 
 
 def build(so=None, defines=()):
@@ -69,7 +70,7 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     keys = host.COMP_KEYS[comp]
     spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
     sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
-    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4, 'pair_ws': 6}[kind]
+    kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4, 'drec': 5, 'pair_ws': 6}[kind]
     if literal:
         kind_i, tw = 0, None   # the C side switches to the literal kind; tile widths of the direct layout
     if tw is None:

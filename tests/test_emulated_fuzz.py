@@ -16,7 +16,7 @@ def test_random_problems_match_oracle(oracle, seed):
         A, tracks, dt, kw = fuzzcases.rand_case(rs)
         with contextlib.redirect_stdout(io.StringIO()):
             ref = oracle.calculate_spectrum(A, tracks, dt, **kw)
-        kinds = ['direct'] if A.get('Features') or A['grid'][-1][0] < 2 else ['direct', 'recur']
+        kinds = ['direct'] if A.get('Features') or A['grid'][-1][0] < 2 else ['direct', 'recur', 'drec']
         if 'recur' in kinds and A.get('mode', 'far') == 'far':
             kinds.append('pair')
             if not kw['comp'].startswith('spheric'):

@@ -199,3 +199,33 @@ def test_warp_specialised_pair_kernel_logic(oracle, grid):
     rad, _ = emu.run(args_si, trs, dts, kind='pair_ws', comp='cartesian_complex')
     for key, r in ref['radiation'].items():
         assert max(rel_errors(rad[key], r)) < 1e-9, (key, rel_errors(rad[key], r))
+
+
+def test_corrected_recurrence_kernel_logic(oracle):
+    """srb_drec.cuh (KIND_DREC): direct layout, per-lane recurrence along omega, per-update correction onto the
+    reference's ROUNDED phase.  The near field of the reference's own near-field test has phases of 1e10 rad (one ulp =
+    2e-6 rad): the rounding of w_j * tau has to be reproduced, not just the exact product.  Also SI-unit far fields
+    (|phase| ~ 1e6), guard-dominated input (partial ranges), snapshots, ragged chunks."""
+    tr, dt, info = cases.undulator_tracks(2, near=True, seed=4)
+    for grid in ((128, 6, 3), (100, 4, 2), (300, 3, 2)):
+        a = cases.undulator_args(info, near=True, grid=grid)
+        for kw in (dict(), dict(comp='cartesian', nSnaps=3), dict(comp='cartesian_complex')):
+            ref = oracle.calculate_spectrum(a, tr, dt, L_screen=1e5, **kw)
+            for nPC in (1, 2):
+                rad, cnt = emu.run(a, tr, dt, kind='drec', L_screen=1e5, nPC=nPC, **kw)
+                for key, r in ref['radiation'].items():
+                    assert max(rel_errors(rad[key], r)) < 3e-10, (grid, kw, key, rel_errors(rad[key], r))
+                assert cnt[0] == ref['passed']
+    trs, dts, infos = cases.wiggler_tracks(4, 256, si_scale=1e-3)
+    args = cases.wiggler_args(infos, grid=(256, 4, 4), si_scale=1e-3)
+    for comp in ('total', 'cartesian_complex', 'spheric'):
+        ref = oracle.calculate_spectrum(args, trs, dts, comp=comp)
+        rad, cnt = emu.run(args, trs, dts, kind='drec', comp=comp)
+        for key, r in ref['radiation'].items():
+            assert max(rel_errors(rad[key], r)) < 1e-12, (comp, key)
+        assert cnt[0] == ref['passed']
+    trb, dtb, infob = cases.betatron_tracks(5, seed=3, samples_per_osc=32)
+    ab = cases.betatron_args(infob, grid=(128, 5, 4))
+    ref = oracle.calculate_spectrum(ab, trb, dtb, comp='cartesian')
+    rad, cnt = emu.run(ab, trb, dtb, kind='drec', comp='cartesian')
+    assert max(max(rel_errors(rad[k], r)) for k, r in ref['radiation'].items()) < 1e-12 and cnt[0] == ref['passed']

@@ -77,7 +77,8 @@ def test_c2_near_undulator(cuda_lib, oracle):
     calc = run_gpu(args, tracks, dt, L_screen=1e5)
     ref = oracle.calculate_spectrum(args, tracks, dt, L_screen=1e5)
     assert_close(calc, ref['radiation'])
-    assert calc.last_run['kernel'] == 'direct'          # omega*L ~ 1e10 rad: recurrence not allowed
+    assert calc.last_run['kernel'] == 'drec'            # omega*L ~ 1e10 rad: corrected recurrence (srb_drec.cuh)
+    assert_close(run_gpu(args, tracks, dt, phasor='direct', L_screen=1e5), ref['radiation'])
     S = calc.Data['radiation']['total'][0]
     kat = json.load(open(os.path.join(GOLD, 'baseline_kat.json')))['C2_near_double']
     for idx, val in kat['spots']:
@@ -442,7 +443,7 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
             if A.get('Features') or A['grid'][-1][0] < 2:
                 phasors = ('auto',)
             else:
-                phasors = ('auto', 'recur', 'direct') if far_plain else ('auto', 'direct')
+                phasors = ('auto', 'recur', 'direct', 'drec') if far_plain else ('auto', 'direct', 'drec')
             for phasor in phasors:
                 calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
                 e = fuzzcases.vector_errors(calc.Data['radiation'], ref['radiation'])

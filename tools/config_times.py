@@ -21,15 +21,20 @@ def run(name, args, tracks, dt, reps=2, **kw):
                          f"integrate_ms={lr['integrate_ms']:.2f} kernel={lr['kernel']} tw={lr['tile_width']} pc={lr['particle_chunks']} guard_pass={f:.4f}\n")
 
 sys.stdout = sys.stderr
+tr1, dt, info = cases.undulator_tracks(1)
+run('C1 (configs[0]) far undulator, single electron (128,32,32) double', cases.undulator_args(info), tr1, dt)
 tr, dt, info = cases.undulator_tracks(24, seed=0)
-run('C1 far undulator 24 e- (128,32,32) double', cases.undulator_args(info), tr, dt)
+run('C1 x 24 e- (the reference test script) double', cases.undulator_args(info), tr, dt)
 a32 = cases.undulator_args(info, dtype='float'); a32['native'] = True
-run('C1 far undulator 24 e- float+native', a32, tr, dt)
+run('C1 x 24 e- float+native', a32, tr, dt)
+trn1, dtn, infon = cases.undulator_tracks(1, near=True)
+run('C2 (configs[1]) near undulator, single electron (128,256,32) double', cases.undulator_args(infon, near=True), trn1, dtn, L_screen=1e5)
 trn, dtn, infon = cases.undulator_tracks(24, near=True, seed=0)
-run('C2 near undulator 24 e- (128,256,32) double', cases.undulator_args(infon, near=True), trn, dtn, L_screen=1e5)
-trw, dtw, infow = cases.wiggler_tracks(1000, 256, seed=0)
-run('C3-like betatron 1e3 x 256 (256,32,32) cartesian double', cases.wiggler_args(infow, grid=(256, 32, 32)), trw, dtw, comp='cartesian')
+run('C2 x 24 e- near double', cases.undulator_args(infon, near=True), trn, dtn, L_screen=1e5)
 trb, dtb, infob = cases.betatron_tracks(1000, seed=0)
-run('C3 betatron recipe (SI) 1e3 x 256 (256,32,32) cartesian double', cases.betatron_args(infob), trb, dtb, comp='cartesian')
-trs, dts, infos = cases.wiggler_tracks(10000, 192, seed=0, K0=4.0, gamma0=200.0)
-run('C4-like spiral 1e4 x 192 (512,64,64) float', cases.wiggler_args(infos, grid=(512, 64, 64), dtype='float'), trs, dts)
+run('C3 (configs[2]) betatron recipe (SI) 1e3 x 256 (256,32,32) cartesian double', cases.betatron_args(infob), trb, dtb, comp='cartesian')
+trs, dts, infos = cases.spiral_tracks(10000, seed=0)
+run('C4 (configs[3]) spiral beam 1e4 x 192 (512,64,64) float, mixed mode', cases.spiral_args(infos), trs, dts)
+lit = cases.spiral_args(infos); lit['float_mode'] = 'literal'
+run('C4 (configs[3]) spiral beam 1e4 x 192 (512,64,64) float, literal mode', lit, trs, dts)
+run('C4 grid, double, coherent (cartesian_complex) as in the notebook', cases.spiral_args(infos, dtype='double'), trs, dts, comp='cartesian_complex')
