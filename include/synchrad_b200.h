@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SRB_ABI_VERSION 2
+#define SRB_ABI_VERSION 3
 
 /* mode: which kernel file of the reference is replaced (calc.py:617-620) */
 #define SRB_MODE_FAR 0  /* kernel_farfield.cl  */
@@ -123,8 +123,9 @@ const char* srb_last_error(void);
  * exist (the reference has no near-field spheric kernels, calc.py:342 would raise). */
 int srb_num_spectra(int mode, int comp);
 
-/* Bytes of scratch srb_integrate wants for this problem (private partial spectra of the
- * particle chunks).  Never fails for valid inputs; 0 is possible. */
+/* Bytes of scratch srb_integrate wants for this problem (pre-pass planes, private partial spectra of the
+ * particle chunks or, with few particles, partial amplitudes of the time segments).  Never fails for valid
+ * inputs; 0 is possible. */
 size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks);
 
 /* The hot path: replaces the whole `for itr in calc_iterator: ... _process_track` loop of
@@ -171,6 +172,8 @@ typedef struct srb_launch_info {
   uint32_t grid_blocks, block_threads, smem_bytes;
   uint32_t kernels_launched;
   uint32_t n_components;  /* far-field amplitude components carried per node (2 transverse | 3) */
+  uint32_t n_time_segments; /* > 1: time-axis split (few particles): every track cut into this many step segments, one
+                               (track, segment) per particle chunk, partial amplitudes summed before squaring */
 } srb_launch_info;
 int srb_last_launch(srb_launch_info* info);
 

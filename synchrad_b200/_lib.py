@@ -55,6 +55,7 @@ class srb_launch_info(ctypes.Structure):
         ('grid_blocks', ctypes.c_uint32), ('block_threads', ctypes.c_uint32),
         ('smem_bytes', ctypes.c_uint32), ('kernels_launched', ctypes.c_uint32),
         ('n_components', ctypes.c_uint32),
+        ('n_time_segments', ctypes.c_uint32),
     ]
 
 

@@ -293,6 +293,7 @@ class SynchRad(Utilities):
             'updates': upd * int(self.Args['numGridNodes']), 'batches': len(batches),
             'kernel': {0: 'direct', 1: 'recurrence', 2: 'literal', 3: 'pair', 4: 'pair_fma', 5: 'drec'}[res.kind], 'integrate_ms': ms,
             'tile_width': int(res.info.tile_width), 'particle_chunks': int(res.info.n_particle_chunks),
+            'time_segments': int(res.info.n_time_segments),
             'grid_blocks': int(res.info.grid_blocks), 'kernels_launched': int(res.info.kernels_launched) + len(keys),
             'h2d_bytes': h2d,
             'd2h_bytes': int(sum(v.nbytes for v in self.Data['radiation'].values())),

@@ -57,7 +57,7 @@ template <class C> constexpr int min_blocks() {
 
 template <class C>
 __global__ void __launch_bounds__(NW * 32, min_blocks<C>()) k_integrate(const srb::Params P) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+  extern __shared__ __align__(128) unsigned char smraw[];
   const uint32_t warp = threadIdx.x >> 5;
   srb::WarpSmem<C>* sm = reinterpret_cast<srb::WarpSmem<C>*>(smraw) + warp;
   const uint32_t nVDtiles = (P.nVD + NW - 1) / NW;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
   uint32_t t0, t1;
   chunk_tracks(P, pc, t0, t1);
   Walk<C> w;
-  w.init(t0, t1);
+  w.init(t0, t1, pc);
   WalkItem it;
   uint32_t k = 0;
 
@@ -344,7 +344,11 @@ __global__ void __launch_bounds__((NCW + NP) * NU * 32, 1) k_integrate_ws(const 
     if (B.valid) mbar_arrive(&S.full[u][sgB]);
     A = nA; B = nB;
   }
-  if (P.counters && nAll) { atomicAdd(P.counters, nPass); atomicAdd(P.counters + 1, nAll); }
+  if (P.counters) {      // one atomic pair per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { nPass += __shfl_xor_sync(0xffffffffu, nPass, o); nAll += __shfl_xor_sync(0xffffffffu, nAll, o); }
+    if (lane == 0 && nAll) { atomicAdd(P.counters, nPass); atomicAdd(P.counters + 1, nAll); }
+  }
 }
 
 // Direction-independent per-step kinematics, once per call (instead of once per direction):
@@ -362,7 +366,6 @@ __global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_
     if (P.mode == srb::MODE_FAR) {
       double av[3] = {0, 0, 0}, bv[3] = {0, 0, 0};
       if (it + 1 < n) srb::far_step_kinematics<double>(P.ux, P.uy, P.uz, i, dtInv, av, bv);
-#pragma unroll
       if (P.prePacked) {      // one record per step for the warp-specialised kernel: one TMA copy stages 34 steps
         double* q = pre + i * 9;
         q[0] = ((const double*)P.x)[i]; q[1] = ((const double*)P.y)[i]; q[2] = ((const double*)P.z)[i];
@@ -423,6 +426,14 @@ __global__ void k_reduce_slabs(srb::Params P, int nOut, size_t perOut) {
     const int c = (int)(i / perOut);
     P.out[c][i - (size_t)c * perOut] += acc;
   }
+}
+
+// time-axis split, second pass (srb_core.cuh: combine_node): thread = (snapshot, node)
+template <int MODE, int NCF>
+__global__ void k_combine_segments(const srb::Params P, size_t n) {
+  if (srb::deselected(P)) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    srb::combine_node<MODE, NCF>(P, i);
 }
 
 __global__ void k_swap_axes(const double* __restrict__ src, double* __restrict__ dst, uint32_t nSnaps,
@@ -518,14 +529,15 @@ struct Launcher {
   int chunk;
   int units;      // virtual directions per block
   int threads;    // block size
+  int minBlocks;  // resident blocks per SM the register budget was tuned for (shared-memory carve-out request)
 };
 
 template <class C> Launcher make_launcher() {
-  return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK, NW, NW * 32};
+  return Launcher{&k_integrate<C>, sizeof(srb::WarpSmem<C>) * NW, C::CHUNK, NW, NW * 32, min_blocks<C>()};
 }
 template <class C, int NU, int NP, int NS, int NCW> Launcher make_launcher_ws() {
   static_assert(sizeof(WsSmem<C, NU, NP, NS>) <= 227 * 1024, "ring does not fit the shared memory of an SM");
-  return Launcher{&k_integrate_ws<C, NU, NP, NS, NCW>, sizeof(WsSmem<C, NU, NP, NS>), C::CHUNK, NU, (NCW + NP) * NU * 32};
+  return Launcher{&k_integrate_ws<C, NU, NP, NS, NCW>, sizeof(WsSmem<C, NU, NP, NS>), C::CHUNK, NU, (NCW + NP) * NU * 32, 1};
 }
 #ifndef SRB_WS_NP
 #define SRB_WS_NP 2     // producer warps per unit
@@ -594,9 +606,11 @@ struct Plan {
   bool native, ws;
   Launcher L;
   uint32_t chunkNodes, nChunks, nVD, nVDtiles, nPC;
+  uint32_t nTS;           // time segments per track (1: off); then nPC = nTracks * nTS and `ampDoubles` replace the slabs
   int blocksPerSM, numSM;
-  size_t perOut, slabDoubles;
+  size_t perOut, slabDoubles, ampDoubles;
   int nOut;
+  size_t work_doubles() const { return nTS > 1 ? ampDoubles : (size_t)(nPC - 1) * slabDoubles; }   // after the pre-pass area
 };
 
 int validate(const srb_grid* g, const srb_tracks* t) {
@@ -695,6 +709,13 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   p->perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
   p->slabDoubles = p->perOut * p->nOut;
   SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->L.smem));
+  {
+    // ask for the L1 / shared-memory split that lets `minBlocks` blocks be resident (the default heuristic gave the
+    // corrected-recurrence kernel 2 blocks per SM where its registers allow 3: profiles/r02_ncu_drec_kernel_first.txt)
+    const size_t want = (p->L.smem + 1024) * (size_t)p->L.minBlocks;
+    const int pct = (int)std::min<size_t>(100, want * 100 / (228 * 1024) + 1);
+    SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, p->L.threads, p->L.smem));
   if (p->blocksPerSM < 1) return fail("kernel does not fit on an SM");
   // particle chunks: fill whole waves of the machine; bounded by tracks, scratch and 64 waves
@@ -713,6 +734,34 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
     if (eff >= best - 1e-12) { best = eff; bestN = (uint32_t)n; }
   }
   p->nPC = bestN;
+  // Time-axis split (the reference's serial loop kernel_farfield.cl:59): with few particles even one track
+  // per block leaves the machine part-empty (single electron on a 128x16x16 grid: 64 blocks of 4 directions for 148
+  // SMs), so every track is cut into nTS segments of whole sub-batches and a second pass squares the summed partial
+  // amplitudes.  A block has a fixed cost (pipeline start-up, flush: ~13 us for the warp-specialised kernel, measured),
+  // so the split is taken only when the particle chunks fill less than 3/4 of the block slots of their waves, with
+  // segments of at least 8 sub-batches.  SRB_TIME_SPLIT=0 disables, =N forces N (tests).
+  p->nTS = 1; p->ampDoubles = 0;
+  if (p->kind != KIND_LITERAL && t->nTracks > 0) {
+    const int ncf = g->mode == SRB_MODE_FAR ? p->nc : 3;
+    const size_t ampPer = (size_t)t->nTracks * g->nSnaps * 2 * ncf * ((size_t)g->nOmega * g->nAxis2 * g->nPhi);   // doubles per segment count
+    const uint64_t capBytes = unlimited ? (1ull << 30) : scratch_bytes;
+    const uint64_t avgSteps = t->totalSteps_host / t->nTracks;
+    const uint64_t fit = std::min<uint64_t>(capBytes / (ampPer * 8),
+                                            std::max<uint64_t>(1, 0x7fffffffull / ((uint64_t)p->nVDtiles * t->nTracks)));
+    uint32_t want = 0;
+    const char* e = std::getenv("SRB_TIME_SPLIT");
+    if (e) want = (uint32_t)std::atoi(e);
+    if (e && want >= 2) p->nTS = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, fit));
+    else if (!e && best < 0.75) {
+      const uint64_t maxTS = std::min<uint64_t>(std::min<uint64_t>(64, avgSteps / 256), fit);
+      auto effOf = [&](uint64_t blocks) { const uint64_t waves = (blocks + slots - 1) / slots; return (double)blocks / (double)(waves * slots); };
+      double bestTS = 0.0;
+      for (uint64_t n = 2; n <= maxTS; n++) bestTS = std::max(bestTS, effOf((uint64_t)p->nVDtiles * t->nTracks * n));
+      for (uint64_t n = 2; n <= maxTS; n++)
+        if (effOf((uint64_t)p->nVDtiles * t->nTracks * n) >= bestTS - 0.02) { if (bestTS > best + 0.1) p->nTS = (uint32_t)n; break; }
+    }
+    if (p->nTS > 1) { p->nPC = t->nTracks * p->nTS; p->ampDoubles = ampPer * p->nTS; }
+  }
   return 0;
 }
 
@@ -740,8 +789,8 @@ size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks) {
   Plan p, q;
   if (make_plan(grid, tracks, 0, true, &p, false) != 0) return 0;
   if (make_plan(grid, tracks, 0, true, &q, true) != 0) return 0;
-  const size_t a = ((size_t)(p.nPC - 1) * p.slabDoubles + p.preDoubles) * sizeof(double);
-  const size_t b = ((size_t)(q.nPC - 1) * q.slabDoubles + q.preDoubles) * sizeof(double);
+  const size_t a = (p.work_doubles() + p.preDoubles) * sizeof(double);
+  const size_t b = (q.work_doubles() + q.preDoubles) * sizeof(double);
   return 64 + std::max(a, b);        // 64-byte header: guard probe counts + on-device kernel choice (phasor = AUTO)
 }
 
@@ -771,6 +820,7 @@ static int launch_plan(const srb_grid* g, const srb_tracks* t, const Plan& p, do
   P.tmaOK = (((uintptr_t)preBuf & 15u) == 0 && !std::getenv("SRB_WS_NOTMA")) ? 1 : 0;      // (env: debugging aid)
   P.prePacked = p.ws ? 1 : 0;
   P.slabs = (double*)scratch + p.preDoubles; P.slabStride = p.slabDoubles; P.nPC = p.nPC;
+  P.nTS = p.nTS; P.amp = p.nTS > 1 ? (double*)scratch + p.preDoubles : nullptr;
   P.counters = (unsigned long long*)counters;
   P.sel = sel; P.selWant = want;
   if (preBuf) {
@@ -780,12 +830,21 @@ static int launch_plan(const srb_grid* g, const srb_tracks* t, const Plan& p, do
     SRB_CUDA(cudaGetLastError());
     (*launched)++;
   }
-  if (p.nPC > 1) SRB_CUDA(cudaMemsetAsync(P.slabs, 0, (size_t)(p.nPC - 1) * p.slabDoubles * sizeof(double), stream));
+  if (p.work_doubles()) SRB_CUDA(cudaMemsetAsync(P.slabs, 0, p.work_doubles() * sizeof(double), stream));
   const uint32_t blocks = p.nVDtiles * p.nPC;
   p.L.kernel<<<blocks, p.L.threads, p.L.smem, stream>>>(P);
   SRB_CUDA(cudaGetLastError());
   (*launched)++;
-  if (p.nPC > 1) {
+  if (p.nTS > 1) {
+    const size_t n = p.perOut;       // (snapshot, node) elements
+    const int rb = (int)std::min<size_t>((n + 127) / 128, (size_t)p.numSM * 16);
+    const int ncf = g->mode == SRB_MODE_FAR ? p.nc : 3;
+    if (g->mode == SRB_MODE_NEAR) k_combine_segments<srb::MODE_NEAR, 3><<<rb, 128, 0, stream>>>(P, n);
+    else if (ncf == 2) k_combine_segments<srb::MODE_FAR, 2><<<rb, 128, 0, stream>>>(P, n);
+    else k_combine_segments<srb::MODE_FAR, 3><<<rb, 128, 0, stream>>>(P, n);
+    SRB_CUDA(cudaGetLastError());
+    (*launched)++;
+  } else if (p.nPC > 1) {
     const size_t n = p.slabDoubles;
     const int rb = (int)std::min<size_t>((n + 255) / 256, (size_t)p.numSM * 8);
     k_reduce_slabs<<<rb, 256, 0, stream>>>(P, p.nOut, p.perOut);
@@ -799,7 +858,7 @@ static void fill_info(const Plan& p, uint32_t launched, int kind) {
   g_info.kind = kind; g_info.tile_width = p.tw; g_info.chunk_nodes = p.chunkNodes; g_info.n_chunks = p.nChunks;
   g_info.n_virtual_dirs = p.nVD; g_info.n_particle_chunks = p.nPC; g_info.grid_blocks = p.nVDtiles * p.nPC;
   g_info.block_threads = (uint32_t)p.L.threads; g_info.n_components = (uint32_t)p.nc; g_info.smem_bytes = (uint32_t)p.L.smem;
-  g_info.kernels_launched = launched;
+  g_info.kernels_launched = launched; g_info.n_time_segments = p.nTS;
 }
 
 int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int n_spectra,

@@ -258,6 +258,11 @@ struct Params {
   // select returns at once (sel == nullptr: unconditional)
   const int32_t* sel;
   int32_t selWant;
+  // time-axis split (few-particle configurations): every track is cut into nTS segments of whole 32-step sub-batches,
+  // particle chunk pc = track * nTS + segment; a flush stores the segment's partial complex amplitudes in `amp`
+  // [(pc * nSnaps + iSnap) * 2 NCF + (Re c | NCF + Im c)][node] and combine_node() squares their sum.  nTS <= 1: off.
+  uint32_t nTS;
+  double* amp;
 };
 SRB_HD bool deselected(const Params& P) { return P.sel != nullptr && *P.sel != P.selWant; }
 
@@ -755,6 +760,51 @@ SRB_HD double* dest(const Params& P, uint32_t pc, int c) {
   return pc == 0 ? P.out[c] : P.slabs + (size_t)(pc - 1) * P.slabStride + (size_t)c * P.nSnaps * nTotal;
 }
 
+// One node's contribution to snapshot iSnap from its complex amplitude (re, im: NCF components in the basis the
+// kernel carries): the epilogues of kernel_farfield.cl:100-106 and its variants.  doRe / doIm: which parts this lane
+// writes (the split layout of the recurrence kernels holds each node in two lanes).
+template <int MODE, int NCF>
+SRB_HD void emit_node(const Params& P, const Geom& g, double w, uint32_t pc, size_t idx, uint32_t j, double* re, double* im,
+                      bool doRe, bool doIm) {
+  const size_t nTotal = (size_t)P.nOmega * P.nA2 * P.nPhi;
+  auto dst = [&](int c) -> double* {
+    return pc == 0 ? P.out[c] : P.slabs + (size_t)(pc - 1) * P.slabStride + (size_t)c * P.nSnaps * nTotal;
+  };
+  const bool cplx = (P.comp == COMP_CART_CPLX || P.comp == COMP_SPH_CPLX);
+  const double wpdt2 = smul(smul(w, P.dt), P.dt);
+  if (MODE == MODE_FAR && NCF == 2) {
+    if (P.comp == COMP_TOTAL) {
+      // |F|^2 in the orthonormal transverse basis
+      if (doRe) dst(0)[idx] += wpdt2 * ((re[0] * re[0] + re[1] * re[1]) + (im[0] * im[0] + im[1] * im[1]));
+      return;
+    }
+    // Cartesian components F = F_theta e_theta + F_phi e_phi
+    const double rt = re[0], rp = re[1], it_ = im[0], ip = im[1];
+    re[0] = rt * g.tx + rp * g.px; re[1] = rt * g.ty + rp * g.py; re[2] = rt * g.tz + rp * g.pz;
+    im[0] = it_ * g.tx + ip * g.px; im[1] = it_ * g.ty + ip * g.py; im[2] = it_ * g.tz + ip * g.pz;
+  }
+  if (!cplx) {
+    if (doRe) {
+      if (P.comp == COMP_TOTAL) {
+        dst(0)[idx] += wpdt2 * (((re[0] * re[0] + re[1] * re[1]) + re[2] * re[2]) +
+                               ((im[0] * im[0] + im[1] * im[1]) + im[2] * im[2]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) dst(c)[idx] += wpdt2 * (re[c] * re[c] + im[c] * im[c]);
+      }
+    }
+  } else {
+    const double wpdt = smul(ssqrt(w), P.dt);
+    const bool useFF = (MODE == MODE_FAR && P.comp == COMP_CART_CPLX && P.formFactor != nullptr);
+    const double ff = useFF ? ((const double*)P.formFactor)[j] : 1.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (doRe) dst(2 * c)[idx] += wpdt * (re[c] * ff);
+      if (doIm) dst(2 * c + 1)[idx] += wpdt * (im[c] * ff);
+    }
+  }
+}
+
 // Split layout (recurrence kernels): lanes l and l^16 hold the cos and sin parts of the same 16
 // tiles, so the partner's accumulators of node k are fetched (GPU: shuffles; emulator: direct
 // read) and both lanes reconstruct the full complex amplitude; lane part 0 then writes.
@@ -771,10 +821,6 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
   const ThreadState<C>& me = st[lane];
 #endif
   const size_t nTotal = (size_t)P.nOmega * P.nA2 * P.nPhi;
-  const bool cplx = (P.comp == COMP_CART_CPLX || P.comp == COMP_SPH_CPLX);
-  const double wpdt2 = smul(smul(tv.w, P.dt), P.dt);
-  const double wpdt = smul(ssqrt(tv.w), P.dt);
-  const bool useFF = (C::MODE == MODE_FAR && P.comp == COMP_CART_CPLX && P.formFactor != nullptr);
   const int tile = (C::KIND == KIND_RECUR) ? (lane & 15) : lane;
   const int part = (C::KIND == KIND_RECUR) ? (lane >> 4) : 0;
 #pragma unroll
@@ -815,36 +861,15 @@ SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint
       }
     }
     if (!valid) continue;
-    if (C::MODE == MODE_FAR && C::NC == 2) {
-      if (P.comp == COMP_TOTAL) {
-        // |F|^2 in the orthonormal transverse basis
-        if (part == 0)
-          dest<C>(P, pc, 0)[idx] += wpdt2 * ((re[0] * re[0] + re[1] * re[1]) + (im[0] * im[0] + im[1] * im[1]));
-        continue;
-      }
-      // Cartesian components F = F_theta e_theta + F_phi e_phi
-      const double rt = re[0], rp = re[1], it_ = im[0], ip = im[1];
-      re[0] = rt * g.tx + rp * g.px; re[1] = rt * g.ty + rp * g.py; re[2] = rt * g.tz + rp * g.pz;
-      im[0] = it_ * g.tx + ip * g.px; im[1] = it_ * g.ty + ip * g.py; im[2] = it_ * g.tz + ip * g.pz;
-    }
-    if (!cplx) {
+    if (P.nTS > 1u) {   // time-axis split: this segment's partial amplitude, squared after the segments are summed
       if (part == 0) {
-        if (P.comp == COMP_TOTAL) {
-          dest<C>(P, pc, 0)[idx] += wpdt2 * (((re[0] * re[0] + re[1] * re[1]) + re[2] * re[2]) +
-                                             ((im[0] * im[0] + im[1] * im[1]) + im[2] * im[2]));
-        } else {
+        double* a = P.amp + (((size_t)pc * P.nSnaps + iSnap) * (size_t)(2 * NCF)) * nTotal + (idx - nTotal * iSnap);
 #pragma unroll
-          for (int c = 0; c < 3; c++) dest<C>(P, pc, c)[idx] += wpdt2 * (re[c] * re[c] + im[c] * im[c]);
-        }
+        for (int c = 0; c < NCF; c++) { a[(size_t)c * nTotal] = re[c]; a[(size_t)(NCF + c) * nTotal] = im[c]; }
       }
-    } else {
-      const double ff = useFF ? (double)((const TI*)P.formFactor)[j] : 1.0;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        if (C::KIND != KIND_RECUR || part == 0) dest<C>(P, pc, 2 * c)[idx] += wpdt * (re[c] * ff);
-        if (C::KIND != KIND_RECUR || part == 1) dest<C>(P, pc, 2 * c + 1)[idx] += wpdt * (im[c] * ff);
-      }
+      continue;
     }
+    emit_node<C::MODE, NCF>(P, g, tv.w, pc, idx, j, re, im, part == 0, C::KIND != KIND_RECUR || part == 1);
   }
 }
 
@@ -875,6 +900,7 @@ SRB_HD void make_geom(const Params& P, uint32_t vd, Geom& g) {
 
 // particle chunk -> track range [t0, t1), balanced by cumulative steps (offsets is a prefix sum)
 SRB_HD void chunk_tracks(const Params& P, uint32_t pc, uint32_t& t0, uint32_t& t1) {
+  if (P.nTS > 1u) { t0 = pc / P.nTS; t1 = t0 + 1u; return; }   // time-axis split: one (track, segment) per chunk
   const uint64_t total = P.offsets[P.nTracks];
   auto bound = [&](uint32_t c) -> uint32_t {
     if (c == 0) return 0u;
@@ -885,6 +911,46 @@ SRB_HD void chunk_tracks(const Params& P, uint32_t pc, uint32_t& t0, uint32_t& t
     return a;
   };
   t0 = bound(pc); t1 = bound(pc + 1);
+}
+
+// time-axis split: loop indices [segLo, segHi) of segment pc % nTS of a track with nComp computed steps -- whole 32-step
+// sub-batches, the same number for every segment (the last ones may be short or empty)
+SRB_HD void seg_range(const Params& P, uint32_t pc, uint32_t nComp, uint32_t& segLo, uint32_t& segHi) {
+  if (P.nTS <= 1u) { segLo = 0u; segHi = 0xffffffffu; return; }
+  const uint32_t seg = pc % P.nTS;
+  const uint32_t nSub = (nComp + (uint32_t)SUB - 1u) / (uint32_t)SUB;
+  const uint32_t per = (nSub + P.nTS - 1u) / P.nTS;
+  const uint64_t lo = (uint64_t)seg * per * SUB, hi = lo + (uint64_t)per * SUB;
+  segLo = lo < nComp ? (uint32_t)lo : nComp;
+  segHi = hi < nComp ? (uint32_t)hi : nComp;
+}
+
+// time-axis split, second pass: element i = (iSnap, node) of the spectra.  Per track (in order: deterministic) the
+// segments' partial amplitudes are summed and the common epilogue adds the track's contribution.  Snapshots that did
+// not fire for a track hold zeros (the buffer is cleared before the integration kernel) and add exactly 0.
+template <int MODE, int NCF>
+SRB_HD void combine_node(const Params& P, size_t i) {
+  const size_t nTotal = (size_t)P.nOmega * P.nA2 * P.nPhi;
+  const size_t iSnap = i / nTotal, node = i - iSnap * nTotal;
+  const uint32_t j = (uint32_t)(node % P.nOmega);
+  const size_t d = node / P.nOmega;
+  Geom g;
+  g.iA2 = (uint32_t)(d % P.nA2); g.iPhi = (uint32_t)(d / P.nA2);
+  g.tx = g.ty = g.tz = g.px = g.py = g.pz = 0.0;
+  if (MODE == MODE_FAR && NCF == 2) {     // e_theta, e_phi as make_geom forms them
+    const double sP = ((const double*)P.sinPhi)[g.iPhi], cP = ((const double*)P.cosPhi)[g.iPhi];
+    const double sT = ((const double*)P.axA)[g.iA2], cT = ((const double*)P.axB)[g.iA2];
+    g.tx = smul(cT, cP); g.ty = smul(cT, sP); g.tz = -sT; g.px = -sP; g.py = cP;
+  }
+  for (uint32_t t = 0; t < P.nTracks; t++) {
+    double re[3] = {0, 0, 0}, im[3] = {0, 0, 0};
+    for (uint32_t s = 0; s < P.nTS; s++) {
+      const double* a = P.amp + ((((size_t)t * P.nTS + s) * P.nSnaps + iSnap) * (size_t)(2 * NCF)) * nTotal + node;
+#pragma unroll
+      for (int c = 0; c < NCF; c++) { re[c] += a[(size_t)c * nTotal]; im[c] += a[(size_t)(NCF + c) * nTotal]; }
+    }
+    emit_node<MODE, NCF>(P, g, ((const double*)P.w)[t], 0u, i, j, re, im, true, true);
+  }
 }
 
 // track t of the batch
@@ -948,13 +1014,16 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
     const uint32_t nComp = tv.n > 0 ? (tv.n - 1 < loopEnd ? tv.n - 1 : loopEnd) : 0;
     uint32_t iSnap = 0;
     while (iSnap < P.nSnaps && !(tv.itStart < tv.snaps[iSnap])) iSnap++;   // :54-57
+    uint32_t segLo, segHi;   // time-axis split: this chunk's share of the steps (everything otherwise)
+    seg_range(P, pc, nComp, segLo, segHi);
     uint32_t cur = 0;    // next loop index `it` to process
     while (iSnap < P.nSnaps) {
       // the flush test `it_glob + 2 == itSnaps[iSnap]` (:100) fires at it = itf, if reachable
       const long long itf = (long long)tv.snaps[iSnap] - 2 - (long long)tv.itStart;
       if (itf < (long long)cur || itf >= (long long)loopEnd) break;   // never fires again (Q3/Q4)
-      const uint32_t stop = (uint32_t)(itf + 1) < nComp ? (uint32_t)(itf + 1) : nComp;
-      for (uint32_t base = cur; base < stop; base += SUB) {
+      uint32_t stop = (uint32_t)(itf + 1) < nComp ? (uint32_t)(itf + 1) : nComp;
+      if (stop > segHi) stop = segHi;
+      for (uint32_t base = cur > segLo ? cur : segLo; base < stop; base += SUB) {
         const int cnt = (int)(stop - base < (uint32_t)SUB ? stop - base : (uint32_t)SUB);
         if constexpr (C::KIND == KIND_LITERAL) {
           SRB_LANES_BEGIN
@@ -1039,7 +1108,12 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
   if (P.counters) {
     SRB_LANES_BEGIN
 #if defined(__CUDA_ARCH__)
-      if (SRB_ST.nAll) { atomicAdd(P.counters, SRB_ST.nPass); atomicAdd(P.counters + 1, SRB_ST.nAll); }
+      // one atomic pair per WARP (32 lanes x thousands of warps on the same two addresses serialise in L2: ~1 ns each,
+      // visible as soon as blocks are short -- the time-axis split)
+      unsigned long long np_ = SRB_ST.nPass, na_ = SRB_ST.nAll;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { np_ += __shfl_xor_sync(0xffffffffu, np_, o); na_ += __shfl_xor_sync(0xffffffffu, na_, o); }
+      if (lane == 0 && na_) { atomicAdd(P.counters, np_); atomicAdd(P.counters + 1, na_); }
 #else
       P.counters[0] += SRB_ST.nPass; P.counters[1] += SRB_ST.nAll;
 #endif

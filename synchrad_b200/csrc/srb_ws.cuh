@@ -80,12 +80,12 @@ struct WalkItem {
 // same item sequence independently.
 template <class C>
 struct Walk {
-  uint32_t t, t1;
+  uint32_t t, t1, pc;
   TrackView tv;       // track of the item returned last
-  uint32_t loopEnd, nComp, iSnap, cur, stop, base, afterFlush;
+  uint32_t loopEnd, nComp, iSnap, cur, stop, base, afterFlush, segLo, segHi;
   int state;          // 0: next track, 1: inside a snapshot interval, 3: open the next interval
   bool fresh;
-  SRB_HD void init(uint32_t t0_, uint32_t t1_) { t = t0_; t1 = t1_; state = 0; fresh = false; }
+  SRB_HD void init(uint32_t t0_, uint32_t t1_, uint32_t pc_) { t = t0_; t1 = t1_; pc = pc_; state = 0; fresh = false; }
   SRB_HD bool next(const Params& P, WalkItem& it) {
     for (;;) {
       if (state == 0) {
@@ -95,6 +95,7 @@ struct Walk {
         nComp = tv.n > 0 ? (tv.n - 1 < loopEnd ? tv.n - 1 : loopEnd) : 0;
         iSnap = 0;
         while (iSnap < P.nSnaps && !(tv.itStart < tv.snaps[iSnap])) iSnap++;   // :54-57
+        seg_range(P, pc, nComp, segLo, segHi);     // time-axis split: this chunk's share of the steps
         cur = 0; fresh = true; state = 3;
       }
       if (state == 3) {
@@ -103,7 +104,8 @@ struct Walk {
         const long long itf = (long long)tv.snaps[iSnap] - 2 - (long long)tv.itStart;
         if (itf < (long long)cur || itf >= (long long)loopEnd) { t++; state = 0; continue; }   // never fires again (Q3/Q4)
         stop = (uint32_t)(itf + 1) < nComp ? (uint32_t)(itf + 1) : nComp;
-        base = cur; afterFlush = (uint32_t)(itf + 1);
+        if (stop > segHi) stop = segHi;
+        base = cur > segLo ? cur : segLo; afterFlush = (uint32_t)(itf + 1);
         state = 1;
       }
       it.iSnap = iSnap; it.newTrack = fresh; fresh = false;
@@ -426,7 +428,7 @@ inline void ws_emulate_task(const Params& P, uint32_t vd, uint32_t pc) {
   WsConst kc;
   ws_const<C>(P, g, kc);
   Walk<C> w;
-  w.init(t0, t1);
+  w.init(t0, t1, pc);
   WalkItem it;
   while (w.next(P, it)) {
     const TrackView& tv = w.tv;

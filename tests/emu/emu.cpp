@@ -52,7 +52,7 @@ extern "C" void srb_emu_sincos(const double* x, double* s, double* c, long n) {
 }
 
 extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra, int nOut,
-                                 int kind, int tw, uint32_t nPC, unsigned long long* counters, int prepass) {
+                                 int kind, int tw, uint32_t nPC, unsigned long long* counters, int prepass, uint32_t nTS) {
   Params P;
   std::memset(&P, 0, sizeof P);
   P.mode = g->mode; P.comp = g->comp;
@@ -78,6 +78,15 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
   const size_t perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
   std::vector<double> slabs((size_t)(nPC > 1 ? nPC - 1 : 0) * perOut * nOut, 0.0);
   P.slabs = slabs.data(); P.slabStride = perOut * nOut; P.nPC = nPC;
+  // time-axis split (nTS > 1): one (track, segment) per chunk, partial amplitudes combined afterwards
+  std::vector<double> amp;
+  P.nTS = nTS > 1 ? nTS : 1;
+  if (nTS > 1) {
+    if (g->dtype == SRB_DTYPE_F32_LITERAL) return -2;
+    P.nPC = nPC = t->nTracks * nTS;
+    amp.assign((size_t)nPC * 6 * perOut, 0.0);
+    P.amp = amp.data();
+  }
   // optional pre-pass planes (same code path the GPU pre-pass kernel uses)
   std::vector<double> pre;
   if (prepass && t->nTracks) {
@@ -146,6 +155,17 @@ extern "C" int srb_emu_integrate(const srb_grid* g, const srb_tracks* t, double*
     }
   }
   if (!ok) return -1;
+  if (nTS > 1) {
+    const bool spheric_ = g->comp == SRB_COMP_SPHERIC || g->comp == SRB_COMP_SPHERIC_COMPLEX;
+    const int ncf = g->mode == SRB_MODE_NEAR ? 3 : (((kind == KIND_RECUR || kind == KIND_PAIR || kind == KIND_PAIR_FMA || ws) && !spheric_) ? 2 : 3);
+    P.counters = nullptr;
+    for (size_t i = 0; i < perOut; i++) {
+      if (g->mode == SRB_MODE_NEAR) combine_node<MODE_NEAR, 3>(P, i);
+      else if (ncf == 2) combine_node<MODE_FAR, 2>(P, i);
+      else combine_node<MODE_FAR, 3>(P, i);
+    }
+    return 0;
+  }
   for (uint32_t s = 0; s + 1 < nPC; s++)
     for (int c = 0; c < nOut; c++)
       for (size_t i = 0; i < perOut; i++) P.out[c][i] += slabs[(size_t)s * P.slabStride + (size_t)c * perOut + i];

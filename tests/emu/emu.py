@@ -28,7 +28,7 @@ def build(so=None, defines=()):
 
 
 def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSnaps=1,
-        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True):
+        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True, nTS=1):
     """Returns (radiation dict in host layout, counters)."""
     build()
     lib = ctypes.CDLL(_SO)
@@ -80,7 +80,7 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     cnt = (ctypes.c_ulonglong * 2)(0, 0)
     lib.srb_emu_integrate.restype = ctypes.c_int
     rc = lib.srb_emu_integrate(ctypes.byref(g), ctypes.byref(t), sp, len(keys), kind_i, int(tw),
-                               ctypes.c_uint32(nPC), cnt, ctypes.c_int(1 if prepass else 0))
+                               ctypes.c_uint32(nPC), cnt, ctypes.c_int(1 if prepass else 0), ctypes.c_uint32(nTS))
     assert rc == 0, 'emulator has no such configuration'
     rad = {k: np.ascontiguousarray(s.swapaxes(-1, -3)) for k, s in zip(keys, spectra)}
     return rad, (cnt[0], cnt[1])

@@ -60,7 +60,7 @@ def test_enum_constants_match_header():
 def test_host_only_entry_points():
     from synchrad_b200 import _lib
     lib = _lib.load()
-    assert lib.srb_version() == 2      # ABI 2: counters[4], on-device kernel choice
+    assert lib.srb_version() == 3      # ABI 3: srb_launch_info.n_time_segments (2: counters[4], on-device kernel choice)
     assert lib.srb_num_spectra(0, 0) == 1 and lib.srb_num_spectra(0, 1) == 3
     assert lib.srb_num_spectra(0, 2) == 6 and lib.srb_num_spectra(0, 4) == 6
     assert lib.srb_num_spectra(1, 3) < 0 and lib.srb_num_spectra(1, 4) < 0   # no near spheric kernels

@@ -229,3 +229,41 @@ def test_corrected_recurrence_kernel_logic(oracle):
     ref = oracle.calculate_spectrum(ab, trb, dtb, comp='cartesian')
     rad, cnt = emu.run(ab, trb, dtb, kind='drec', comp='cartesian')
     assert max(max(rel_errors(rad[k], r)) for k, r in ref['radiation'].items()) < 1e-12 and cnt[0] == ref['passed']
+
+
+@pytest.mark.parametrize('comp', ['total', 'cartesian_complex', 'spheric'])
+def test_time_axis_split_far(oracle, comp):
+    """Time-axis split (few-particle configurations): every track cut into nTS step segments, partial complex
+    amplitudes summed before squaring.  Snapshots (cumulative), late it_start, tracks of different lengths, every
+    far-field kernel form; the passed-update counts must not change."""
+    tr, dt, info = cases.undulator_tracks(3, seed=4)
+    tr[1] = [np.asarray(a)[:700].copy() if isinstance(a, np.ndarray) else a for a in tr[1]]     # a shorter track
+    tr2 = [t[:7] + [s] for t, s in zip(tr, [0, 7, 40])]
+    args = cases.undulator_args(info, grid=(70, 3, 2))
+    kw = dict(comp=comp, nSnaps=3, it_range=(2, 1600), sigma_particle=2e-5)
+    ref = oracle.calculate_spectrum(args, tr2, dt, **kw)
+    kinds = ['direct', 'recur', 'pair', 'drec'] + (['pair_ws'] if not comp.startswith('spheric') else [])
+    base = None
+    for kind in kinds:
+        for nTS in (3, 5):
+            rad, cnt = emu.run(args, tr2, dt, kind=kind, nTS=nTS, **kw)
+            for key, r in ref['radiation'].items():
+                assert max(rel_errors(rad[key], r)) < 1e-10, (kind, nTS, key, rel_errors(rad[key], r))
+            base = base or cnt
+            assert cnt == base, (kind, nTS, cnt, base)
+    assert base[1] > 0
+
+
+def test_time_axis_split_near_and_per_track_ranges(oracle):
+    tr, dt, info = cases.undulator_tracks(2, near=True, seed=2)
+    args = cases.undulator_args(info, near=True, grid=(40, 3, 2))
+    for kind in ('direct', 'drec'):
+        ref = oracle.calculate_spectrum(args, tr, dt, comp='cartesian', L_screen=1e5, nSnaps=2)
+        rad, _ = emu.run(args, tr, dt, kind=kind, nTS=4, comp='cartesian', L_screen=1e5, nSnaps=2)
+        for key, r in ref['radiation'].items():
+            assert max(rel_errors(rad[key], r)) < 1e-9, (kind, key)
+    args = cases.undulator_args(info, near=True, grid=(64, 3, 2), L_scr=2.0)
+    args['grid'][0] = (1.0, 40.0)
+    ref = oracle.calculate_spectrum(args, tr, dt, L_screen=2.0)
+    rad, _ = emu.run(args, tr, dt, kind='recur', nTS=7, L_screen=2.0)
+    assert max(rel_errors(rad['total'], ref['radiation']['total'])) < 1e-10

@@ -61,6 +61,49 @@ def test_c1_far_undulator_full_grid(cuda_lib, oracle, phasor):
     assert abs(abs(E - Et) / Et * 100 - kat['deviation_percent']) < 1e-3   # prints 1.07 % like the reference
 
 
+def test_time_axis_split_single_electron(cuda_lib, oracle):
+    """configs[0] with ONE electron: when the blocks of one track fill less than 3/4 of the machine's block slots the
+    planner cuts the track into step segments (partial amplitudes summed before squaring); same result, same guard
+    counts.  Full grid: 256 blocks -- the warp-specialised pair kernel (148 slots, 86 %) stays unsplit, the recurrence
+    kernel (592 slots) splits; 128x16x16: 64 blocks, both split."""
+    tracks, dt, info = cases.undulator_tracks(1)
+    for grid, expect in (((128, 32, 32), {'auto': False, 'recur': True}), ((128, 16, 16), {'auto': True, 'recur': True, 'direct': True})):
+        args = cases.undulator_args(info, grid=grid)
+        ref = oracle.calculate_spectrum(args, tracks, dt)
+        for phasor, split in expect.items():
+            calc = run_gpu(args, tracks, dt, phasor=phasor)
+            assert (calc.last_run['time_segments'] > 1) == split, (grid, phasor, calc.last_run)
+            assert_close(calc, ref['radiation'], what=(grid, phasor))
+            assert calc.last_run['passed_updates'] == ref['passed']
+            assert calc.last_run['updates'] == ref['updates']
+
+
+@pytest.mark.parametrize('near', [False, True])
+def test_time_axis_split_forced(cuda_lib, oracle, monkeypatch, near):
+    """Forced split (SRB_TIME_SPLIT=5) on every kernel form with snapshots, a late it_start and a shorter track."""
+    tr, dt, info = cases.undulator_tracks(3, near=near, seed=4)
+    tr[1] = [np.asarray(a)[:700].copy() if isinstance(a, np.ndarray) else a for a in tr[1]]
+    tr = [t[:7] + [s] for t, s in zip(tr, [0, 7, 40])]
+    args = cases.undulator_args(info, near=near, grid=(100, 6, 4))
+    kw = dict(nSnaps=3, it_range=(2, 1600))
+    if near:
+        kw['L_screen'] = 1e5
+    for comp in (['total', 'cartesian_complex'] if near else ['total', 'cartesian_complex', 'spheric']):
+        ref = oracle.calculate_spectrum(args, tr, dt, comp=comp, **kw)
+        for phasor in (['auto', 'direct'] if near else ['auto', 'pair_fma', 'recur', 'direct', 'drec']):
+            monkeypatch.setenv('SRB_TIME_SPLIT', '0')
+            one = run_gpu(args, tr, dt, phasor=phasor, comp=comp, **kw)
+            assert one.last_run['time_segments'] == 1
+            monkeypatch.setenv('SRB_TIME_SPLIT', '5')
+            calc = run_gpu(args, tr, dt, phasor=phasor, comp=comp, **kw)
+            assert calc.last_run['time_segments'] == 5, calc.last_run
+            assert_close(calc, ref['radiation'], what=(comp, phasor))
+            # (the kernels skip the steps after a track's last reachable flush, the oracle counts them: compare the two runs)
+            assert calc.last_run['passed_updates'] == one.last_run['passed_updates']
+            assert calc.last_run['visited_updates'] == one.last_run['visited_updates']
+            monkeypatch.delenv('SRB_TIME_SPLIT')
+
+
 def test_c1_24_particles_seeded(cuda_lib, oracle):
     tracks, dt, info = cases.undulator_tracks(24, seed=0)
     args = cases.undulator_args(info, grid=(128, 16, 8))
