@@ -140,7 +140,7 @@ def _child_setup():
             tw = next((o for o in (2, 4, 8) if 32 * o >= grid.nOmega), 8)
             cnt = (ctypes.c_ulonglong * 2)(0, 0)
             rc = emu.srb_emu_integrate(ctypes.byref(grid), ctypes.byref(tracks), spectra_ptrs, n_spectra, 0, tw,
-                                       ctypes.c_uint32(1), cnt, ctypes.c_int(1))
+                                       ctypes.c_uint32(1), cnt, ctypes.c_int(1), ctypes.c_uint32(1))
             if rc != 0:
                 raise RuntimeError('emulator has no such configuration')
         pyopencl._integrate_host = emu_integrate_host

@@ -88,7 +88,7 @@ def test_binding_glue_with_emulated_kernels(oracle, monkeypatch):
         tw = next((o for o in (2, 4, 8) if 32 * o >= grid.nOmega), 8)
         cnt = (ctypes.c_ulonglong * 2)(0, 0)
         assert lib.srb_emu_integrate(ctypes.byref(grid), ctypes.byref(tracks), spectra_ptrs, n_spectra, 0, tw,
-                                     ctypes.c_uint32(1), cnt, ctypes.c_int(1)) == 0
+                                     ctypes.c_uint32(1), cnt, ctypes.c_int(1), ctypes.c_uint32(1)) == 0
     monkeypatch.setattr(cl, '_integrate_host', emu_integrate_host)
     stored = np.load(os.path.join(GOLD, 'reference_cases.npz'))
     meta = json.load(open(os.path.join(GOLD, 'reference_cases_meta.json')))
