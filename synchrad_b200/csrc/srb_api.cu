@@ -709,14 +709,19 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   p->perOut = (size_t)g->nSnaps * g->nOmega * g->nAxis2 * g->nPhi;
   p->slabDoubles = p->perOut * p->nOut;
   SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->L.smem));
-  {
-    // ask for the L1 / shared-memory split that lets `minBlocks` blocks be resident (the default heuristic gave the
-    // corrected-recurrence kernel 2 blocks per SM where its registers allow 3: profiles/r02_ncu_drec_kernel_first.txt)
+  SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, p->L.threads, p->L.smem));
+  if (p->blocksPerSM < p->L.minBlocks) {
+    // the default L1 / shared-memory split leaves fewer resident blocks than the registers were tuned for (seen on the
+    // corrected-recurrence kernel: 2 instead of 3): ask for the carve-out that fits them.  Only then -- the kernels
+    // that stream tracks through L1 lose ~8 % with a smaller L1 (C4 recipe, profiles/r02_guard_dominated.md).
     const size_t want = (p->L.smem + 1024) * (size_t)p->L.minBlocks;
     const int pct = (int)std::min<size_t>(100, want * 100 / (228 * 1024) + 1);
-    SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    const char* ce = std::getenv("SRB_CARVEOUT");             // (0: leave the driver's default; A/B measurements)
+    if (!(ce && std::atoi(ce) == 0)) {
+      SRB_CUDA(cudaFuncSetAttribute(p->L.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, p->L.threads, p->L.smem));
+    }
   }
-  SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->blocksPerSM, p->L.kernel, p->L.threads, p->L.smem));
   if (p->blocksPerSM < 1) return fail("kernel does not fit on an SM");
   // particle chunks: fill whole waves of the machine; bounded by tracks, scratch and 64 waves
   const uint64_t slots = (uint64_t)p->numSM * p->blocksPerSM;

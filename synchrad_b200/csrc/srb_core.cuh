@@ -530,13 +530,24 @@ SRB_HD void make_seeds(const Params& P, const Geom& g, double tau, WarpSmem<C>& 
   }
 }
 
+// The prep phase of one step (lane = step) in two parts.
+//   prep_guard: tau, the Nyquist pass range and flag (0 nothing passes, 1 all nodes of the chunk, 2 some, 3 = 1|2 with a
+//               phase too large for the seed arithmetic), the amplitude vector -- everything stays in registers;
+//   prep_store: phasor seeds and the shared-memory record for the lane = tile main phases.
+// Between the two the warp may decide to evaluate a guard-dominated sub-batch with lane = step (main_sparse below),
+// which needs neither seeds nor records.
+struct PrepStep { uint32_t flag, lo, hi; double tau, V[6]; };
+
 template <class C>
-SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, uint32_t itBase, int cnt,
-                           double dtInv, int lane, WarpSmem<C>& sm, ThreadState<C>& st) {
+SRB_HD void prep_guard(const Params& P, const Geom& g, const TrackView& tv, uint32_t itBase, int cnt,
+                       double dtInv, int lane, ThreadState<C>& st, PrepStep& ps) {
   using TM = typename C::TM;
-  if (lane >= cnt) return 0u;
+  ps.flag = ps.lo = ps.hi = 0u; ps.tau = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) ps.V[k] = 0.0;
+  if (lane >= cnt) return;
   const uint32_t it = itBase + (uint32_t)lane;
-  double tau, tauPrev, V[6] = {0, 0, 0, 0, 0, 0};
+  double tau, tauPrev;
   double r0 = 0, r1 = 0, r2 = 0, rL = 1;
   if (C::MODE == MODE_FAR) tau = far_tau<C>(P, g, tv, it);
   else near_tau<C>(P, g, tv, it, tau, r0, r1, r2, rL);
@@ -555,41 +566,163 @@ SRB_HD uint32_t prep_phase(const Params& P, const Geom& g, const TrackView& tv, 
   const uint32_t n = g.cHi - g.cLo;
   uint32_t flag = (hi <= lo) ? 0u : ((lo == 0 && hi == n) ? 1u : 2u);
   st.nAll += n;
-  if (flag == 0u) { sm.rng[lane] = 0u; return 0u; }   // nothing passes the guard: no amplitude, no seeds
-  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, V);
-  else prep_near<C>(P, g, tv, it, r0, r1, r2, rL, V, V + 3);
-  double last[3] = {tau, 0.0, 0.0};
-  if constexpr (C::PAIR) {
-    const double wl = (double)((const typename C::TI*)P.omega)[g.cHi - 1];
-    if (sizeof(TM) == 8 && fabs(wl * tau) > 262144.0) flag = 3u;
-    else make_seeds_pair<C>(P, g, tau, V, sm, lane);
-  }
-  if (C::KIND == KIND_RECUR) {
-    // The recurrence reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
+  ps.tau = tau;
+  if (flag == 0u) return;                              // nothing passes the guard: no amplitude, no seeds
+  if (C::MODE == MODE_FAR) prep_far<C>(P, g, tv, it, dtInv, ps.V);
+  else prep_near<C>(P, g, tv, it, r0, r1, r2, rL, ps.V, ps.V + 3);
+  if (C::PAIR || C::KIND == KIND_RECUR) {
+    // The seed arithmetic reproduces the reference's rounded phase fl(w_j*tau) only to ~4 ulp(phase);
     // beyond |phase| ~ 2^18 that exceeds the 1e-9 parity budget, so such steps are evaluated
     // node by node (flag 3).  fp32 main phase: the seeds are fp64, no such limit.
     const double wl = (double)((const typename C::TI*)P.omega)[P.descending ? g.cLo : g.cHi - 1];
-    const bool big = sizeof(TM) == 8 && fabs(wl * tau) > 262144.0;
-    if (big) flag = 3u; else make_seeds<C>(P, g, tau, sm, lane, last);
+    if (sizeof(TM) == 8 && fabs(wl * tau) > 262144.0) flag = 3u;
+  }
+  ps.flag = flag; ps.lo = lo; ps.hi = hi;
+  st.nPass += hi - lo;
+}
+
+template <class C>
+SRB_HD void prep_store(const Params& P, const Geom& g, const PrepStep& ps, int cnt, int lane, WarpSmem<C>& sm) {
+  using TM = typename C::TM;
+  if (lane >= cnt) return;
+  const uint32_t flag = ps.flag;
+  if (flag == 0u) { sm.rng[lane] = 0u; return; }
+  const double tau = ps.tau;
+  double last[3] = {tau, 0.0, 0.0};
+  if constexpr (C::PAIR) {
+    if (flag != 3u) make_seeds_pair<C>(P, g, tau, ps.V, sm, lane);
+  }
+  if (C::KIND == KIND_RECUR) {
+    if (flag != 3u) make_seeds<C>(P, g, tau, sm, lane, last);
   }
   if constexpr (C::KIND == KIND_DREC) {
     double w4[4];
     make_seeds_drec<C>(P, g, tau, sm, lane, w4);
     sm.rec[lane][C::NV + 1] = w4[0]; sm.rec[lane][C::NV + 2] = w4[1]; sm.rec[lane][C::NV + 3] = w4[2]; sm.rec[lane][C::NV + 4] = w4[3];
   }
-  sm.rng[lane] = lo | (hi << 10) | (flag << 30);
-  st.nPass += hi - lo;
+  sm.rng[lane] = ps.lo | (ps.hi << 10) | (flag << 30);
 #pragma unroll
-  for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)V[k];
+  for (int k = 0; k < C::NV; k++) sm.rec[lane][k] = (TM)ps.V[k];
   if (!C::PAIR || flag == 3u)
     sm.rec[lane][C::NV] = (TM)last[0];   // recurrence: 2cos(d) (flag 3: tau) ; direct: tau ; pair: flag 3 only
   if (C::KIND == KIND_DIRECT && sizeof(TM) == 4)
     sm.rec[lane][C::NV + 1] = (TM)ssub(tau, (double)(TM)tau);   // fp32 direct: tau = hi + lo (48 bits)
   if (C::KIND == KIND_RECUR) { sm.rec[lane][C::NV + 1] = (TM)last[1]; sm.rec[lane][C::NV + 2] = (TM)last[2]; }
-  return flag;
 }
 
+// Guard-dominated sub-batches (wiggler / betatron regime: a few low-omega nodes pass at every step) on the recurrence
+// kernels: the lane = tile main phase walks the 32 steps one after the other with a handful of lanes busy.  Here the
+// lanes stay the STEPS: for every chunk node j below the largest pass bound of the sub-batch each lane evaluates its
+// step's phasor at the reference's rounded phase (sincos_big of fl(w_j*tau): exact at any magnitude, so SI-unit
+// phases need no special case) times its amplitude, the warp sums the 2 NV products, and the node's two owner
+// lanes (cos part, sin part of tile j % 16) take them.  ~100 instructions per node instead of ~80 per step.
+// decision thresholds: instructions per node of the lane = step evaluation relative to the model of the lane = tile
+// partial loop below, for steps with huge phases (per-node sincos in both forms) and ordinary ones (recurrence in the
+// lane = tile form); measured on the C3 / C4 recipes (profiles/r02_guard_dominated.md)
+#ifndef SRB_SPARSE_COST_BIG
+#define SRB_SPARSE_COST_BIG 60
+#endif
+#ifndef SRB_SPARSE_COST_SMALL
+#define SRB_SPARSE_COST_SMALL 400    // (C4 recipe: the recurrence form of the lane = tile loop is hard to beat)
+#endif
+#ifndef SRB_SPARSE_HMAX
+#define SRB_SPARSE_HMAX 8            // steps with at most this many passing nodes may be split off a mixed sub-batch
+#endif
+SRB_HD bool sparse_pays(uint32_t maxHi, uint32_t nAny, bool big) {
+  const uint32_t kmax = (maxHi + 15u) / 16u;
+  const uint32_t dense = nAny * (50u + (big ? 40u : 8u) * kmax);
+  return maxHi * (uint32_t)(big ? SRB_SPARSE_COST_BIG : SRB_SPARSE_COST_SMALL) + 64u < dense;
+}
+#if defined(__CUDA_ARCH__)
+template <class C>
+SRB_HD void main_sparse(const Params& P, const Geom& g, const PrepStep& ps, uint32_t hi, uint32_t maxHi, int lane,
+                        WarpSmem<C>& sm, ThreadState<C>& st) {     // hi: this lane's pass bound, 0 if its step is not taken here
+  using TI = typename C::TI; using TM = typename C::TM;
+  constexpr int NV = C::NV, TW = C::TW;
+  // G nodes at a time: each lane (= step) stores its G * 2 NV products (V_c cos, V_c sin) as columns of a [value][lane]
+  // array in the (idle) staging area; lane L then sums half L & 1 of row L >> 1, one shuffle joins the halves, and the
+  // owner lanes of the G nodes fetch their NV sums: ~12 instructions per node for the reduction against 60 for a
+  // shuffle butterfly of every value.
+  constexpr int G = NV == 2 ? 4 : (NV == 3 ? 2 : 1), NVAL = G * 2 * NV, ROW = 33;
+  static_assert(NVAL <= 16 && 16 % G == 0, "one row per lane pair");
+  static_assert(sizeof(WarpSmem<C>) >= (size_t)NVAL * ROW * sizeof(double), "staging area too small for the sparse reduction");
+  double* buf = reinterpret_cast<double*>(&sm);
+  const uint32_t mine = (uint32_t)(lane & 15);
+  const int part = lane >> 4, row = lane >> 1, half = lane & 1;
+  const uint32_t jLast = g.cHi - g.cLo - 1u;
+  for (uint32_t k = 0; 16u * k < maxHi; k++) {
+    double tmp[NV];
+#pragma unroll
+    for (int c = 0; c < NV; c++) tmp[c] = 0.0;
+    for (uint32_t m0 = 0; m0 < 16u && 16u * k + m0 < maxHi; m0 += (uint32_t)G) {
+#pragma unroll
+      for (int q = 0; q < G; q++) {
+        const uint32_t j = 16u * k + m0 + (uint32_t)q;
+        double sn, cs;
+        sincos_big(smul((double)((const TI*)P.omega)[g.cLo + (j < jLast ? j : jLast)], ps.tau), &sn, &cs);
+        if (!(j < hi)) { sn = 0.0; cs = 0.0; }
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+          buf[(q * 2 * NV + c) * ROW + lane] = ps.V[c] * cs;
+          buf[(q * 2 * NV + NV + c) * ROW + lane] = ps.V[c] * sn;
+        }
+      }
+      __syncwarp();
+      double tot = 0.0;
+      if (row < NVAL) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) tot += buf[row * ROW + half * 16 + i];
+      }
+      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+      const int q = (int)mine - (int)m0;        // index of the node this lane owns in the group, if it is in it
+      const bool owns = q >= 0 && q < G;
+#pragma unroll
+      for (int c = 0; c < NV; c++) {
+        const double f = __shfl_sync(0xffffffffu, tot, 2 * ((owns ? q : 0) * 2 * NV + part * NV + c));
+        if (owns) tmp[c] = f;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int kk = 0; kk < TW; kk++) {
+      if ((uint32_t)kk == k) {        // warp-uniform
+#pragma unroll
+        for (int c = 0; c < NV; c++) st.acc[kk * NV + c] += (TM)tmp[c];
+      }
+    }
+  }
+}
+#else
+template <class C>
+inline void main_sparse(const Params& P, const Geom& g, const PrepStep* ps, uint32_t maxHi, ThreadState<C>* st) {
+  using TI = typename C::TI; using TM = typename C::TM;
+  constexpr int NV = C::NV;
+  for (uint32_t j = 0; j < maxHi; j++) {
+    double a[NV], b[NV];
+    for (int c = 0; c < NV; c++) a[c] = b[c] = 0.0;
+    for (int lane = 0; lane < 32; lane++) {
+      if (!ps[lane].flag || j >= ps[lane].hi) continue;
+      double sn, cs;
+      sincos_big(smul((double)((const TI*)P.omega)[g.cLo + j], ps[lane].tau), &sn, &cs);
+      for (int c = 0; c < NV; c++) { a[c] += ps[lane].V[c] * cs; b[c] += ps[lane].V[c] * sn; }
+    }
+    for (int c = 0; c < NV; c++) {
+      st[j & 15u].acc[(j >> 4) * NV + c] += (TM)a[c];
+      st[(j & 15u) + 16u].acc[(j >> 4) * NV + c] += (TM)b[c];
+    }
+  }
+}
+#endif
+
 // -------------------------------------------------------------------------------- main phase
+// index of the lowest set bit (warp-uniform step masks are walked bit by bit instead of testing all 32 steps)
+SRB_HD int low_bit(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
 // smallest tile-local index k with m + T*k >= j (chunk-relative node bound j >= 0): ceil((j-m)/T)
 SRB_HD int tile_lo(int j, int m, int T) { const int d = j - m; return d <= 0 ? 0 : (d + T - 1) / T; }
 
@@ -643,8 +776,8 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     }
     return;
   }
-  for (int s = 0; s < cnt; s++) {
-    if (!((anyMask >> s) & 1u)) continue;   // warp-uniform: nothing passes the guard at this step
+  for (uint32_t todo = anyMask; todo; todo &= todo - 1u) {   // steps where anything passes the guard (warp-uniform)
+    const int s = low_bit(todo);
     const uint32_t r = sm.rng[s];
     const uint32_t flag = r >> 30;
     TM V[NV];
@@ -656,15 +789,22 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     const int kmax = tile_lo((int)((r >> 10) & 0x3ffu), 0, 16);
     if (flag == 3) {   // direct evaluation of this step (phase too large for the recurrence)
       const uint32_t j0 = g.cLo + (uint32_t)m;
-#pragma unroll
-      for (int k = 0; k < TW; k++) {
-        if (k >= kmax) break;                      // warp-uniform
+      // (a rolled loop over k with a warp-uniform accumulator switch: this rare path is kept small -- the kernel's
+      //  top stall was instruction fetch, profiles/r02_ncu_c3_recurrence_kernel.txt)
+#pragma unroll 1
+      for (int k = 0; k < kmax && k < TW; k++) {
+        TM cur = (TM)0;
         if (k >= lo && k < hi) {
           TM sn, cs;
           sincos_t(tmul((TM)((const TI*)P.omega)[j0 + 16 * k], coef), &sn, &cs);   // coef slot holds tau
-          const TM cur = (lane >> 4) ? sn : cs;
+          cur = (lane >> 4) ? sn : cs;
+        }
 #pragma unroll
-          for (int c = 0; c < NV; c++) st.acc[k * NV + c] = fma(V[c], cur, st.acc[k * NV + c]);
+        for (int kk = 0; kk < TW; kk++) {
+          if (kk == k) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) st.acc[kk * NV + c] = fma(V[c], cur, st.acc[kk * NV + c]);
+          }
         }
       }
       continue;
@@ -731,8 +871,8 @@ SRB_HD void main_direct(const Params& P, const Geom& g, const WarpSmem<C>& sm, i
     }
     return;
   }
-  for (int s = 0; s < cnt; s++) {
-    if (!((anyMask >> s) & 1u)) continue;
+  for (uint32_t todo = anyMask; todo; todo &= todo - 1u) {
+    const int s = low_bit(todo);
     const uint32_t r = sm.rng[s];
     const int lo = tile_lo((int)(r & 0x3ffu), lane, 32), hi = tile_lo((int)((r >> 10) & 0x3ffu), lane, 32);
     if (hi <= 0 || lo >= TW) continue;
@@ -1051,14 +1191,86 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
         }
 #endif
         uint32_t fullMask = 0u, anyMask = 0u;   // bit s: step s of the sub-batch is all-pass / has any pass
-        SRB_LANES_BEGIN
-          const uint32_t fl = prep_phase<C>(P, g, tv, base, cnt, dtInv, lane, sm, SRB_ST);
+        // recurrence kernels: steps where only a few low nodes pass (hi <= SRB_SPARSE_HMAX), or the whole sub-batch when
+        // no step passes everywhere and it is cheaper, go through the lane = step evaluation (main_sparse); the others
+        // through seeds + shared-memory records + the lane = tile main phase
+        uint32_t sparseMask = 0u, maxHi = 0u;
 #if defined(__CUDA_ARCH__)
-          fullMask = __ballot_sync(0xffffffffu, fl == 1u);
-          anyMask = __ballot_sync(0xffffffffu, fl != 0u);
+        PrepStep psv[1];
 #else
-          if (fl == 1u) fullMask |= 1u << lane;
-          if (fl != 0u) anyMask |= 1u << lane;
+        PrepStep psv[32];
+        uint32_t bigMask = 0u;
+#endif
+        SRB_LANES_BEGIN
+#if defined(__CUDA_ARCH__)
+          PrepStep& ps = psv[0];
+#else
+          PrepStep& ps = psv[lane];
+#endif
+          prep_guard<C>(P, g, tv, base, cnt, dtInv, lane, SRB_ST, ps);
+#if defined(__CUDA_ARCH__)
+          fullMask = __ballot_sync(0xffffffffu, ps.flag == 1u);
+          anyMask = __ballot_sync(0xffffffffu, ps.flag != 0u);
+          if constexpr (C::KIND == KIND_RECUR) {
+            if (anyMask != fullMask) {
+              const uint32_t bigMask = __ballot_sync(0xffffffffu, ps.flag == 3u);
+              const bool small = ps.flag != 0u && ps.hi <= (uint32_t)SRB_SPARSE_HMAX;
+              const uint32_t smallMask = __ballot_sync(0xffffffffu, small);
+              if (fullMask == 0u && (bigMask & anyMask) == 0u) {     // (ordinary phases: the whole sub-batch or nothing)
+                const uint32_t mh = __reduce_max_sync(0xffffffffu, ps.flag ? ps.hi : 0u);
+                if (sparse_pays(mh, (uint32_t)__popc(anyMask), false)) { sparseMask = anyMask; maxHi = mh; }
+              } else if (fullMask == 0u) {
+                const uint32_t mh = __reduce_max_sync(0xffffffffu, ps.flag ? ps.hi : 0u);
+                if (sparse_pays(mh, (uint32_t)__popc(anyMask), true)) { sparseMask = anyMask; maxHi = mh; }
+              }
+              if (!sparseMask && smallMask && (bigMask & smallMask)) {
+                const uint32_t mh = __reduce_max_sync(0xffffffffu, small ? ps.hi : 0u);
+                if (sparse_pays(mh, (uint32_t)__popc(smallMask), true)) { sparseMask = smallMask; maxHi = mh; }
+              }
+            }
+          }
+#else
+          if (ps.flag == 1u) fullMask |= 1u << lane;
+          if (ps.flag != 0u) anyMask |= 1u << lane;
+          if (ps.flag == 3u) bigMask |= 1u << lane;
+#endif
+        SRB_LANES_END
+#if defined(SRB_SKIP_MAIN)      // tuning aid: the cost of the guard part of the prep phase alone
+        continue;
+#endif
+#if !defined(__CUDA_ARCH__)
+        if (C::KIND == KIND_RECUR && anyMask != fullMask) {      // the same decision, lanes as a loop
+          uint32_t smallMask = 0u, mhAll = 0u, mhSmall = 0u;
+          for (int l = 0; l < 32; l++) {
+            if (!psv[l].flag) continue;
+            if (psv[l].hi > mhAll) mhAll = psv[l].hi;
+            if (psv[l].hi <= (uint32_t)SRB_SPARSE_HMAX) { smallMask |= 1u << l; if (psv[l].hi > mhSmall) mhSmall = psv[l].hi; }
+          }
+          if (fullMask == 0u && sparse_pays(mhAll, (uint32_t)__builtin_popcount(anyMask), (bigMask & anyMask) != 0u)) { sparseMask = anyMask; maxHi = mhAll; }
+          if (!sparseMask && smallMask && (bigMask & smallMask) && sparse_pays(mhSmall, (uint32_t)__builtin_popcount(smallMask), true)) { sparseMask = smallMask; maxHi = mhSmall; }
+        }
+#endif
+        if constexpr (C::KIND == KIND_RECUR) {
+          if (sparseMask) {
+#if defined(__CUDA_ARCH__)
+            const bool taken = (sparseMask >> (threadIdx.x & 31u)) & 1u;
+            main_sparse<C>(P, g, psv[0], taken ? psv[0].hi : 0u, maxHi, (int)(threadIdx.x & 31u), sm, st[0]);
+            if (taken) psv[0].flag = 0u;
+            __syncwarp();
+#else
+            PrepStep sel[32];
+            for (int l = 0; l < 32; l++) { sel[l] = psv[l]; if (!((sparseMask >> l) & 1u)) sel[l].flag = 0u; else psv[l].flag = 0u; }
+            main_sparse<C>(P, g, sel, maxHi, st);
+#endif
+            anyMask &= ~sparseMask;
+            if (!anyMask) continue;
+          }
+        }
+        SRB_LANES_BEGIN
+#if defined(__CUDA_ARCH__)
+          prep_store<C>(P, g, psv[0], cnt, lane, sm);
+#else
+          prep_store<C>(P, g, psv[lane], cnt, lane, sm);
 #endif
         SRB_LANES_END
 #if !defined(__CUDA_ARCH__)

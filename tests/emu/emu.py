@@ -28,10 +28,11 @@ def build(so=None, defines=()):
 
 
 def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSnaps=1,
-        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True, nTS=1):
-    """Returns (radiation dict in host layout, counters)."""
-    build()
-    lib = ctypes.CDLL(_SO)
+        sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True, nTS=1, variant=None):
+    """Returns (radiation dict in host layout, counters).  variant = (name, defines): a separately built emulator."""
+    so = _SO if variant is None else os.path.join(_HERE, f'libsrb_emu_{variant[0]}.so')
+    build(so, () if variant is None else variant[1])
+    lib = ctypes.CDLL(so)
     A = dict(Args)
     A, dtype = host.init_args(A)
     A['sigma_particle'] = dtype(sigma_particle)

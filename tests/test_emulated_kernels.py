@@ -267,3 +267,35 @@ def test_time_axis_split_near_and_per_track_ranges(oracle):
     ref = oracle.calculate_spectrum(args, tr, dt, L_screen=2.0)
     rad, _ = emu.run(args, tr, dt, kind='recur', nTS=7, L_screen=2.0)
     assert max(rel_errors(rad['total'], ref['radiation']['total'])) < 1e-10
+
+
+def test_guard_dominated_sub_batches_lane_is_step(oracle):
+    """Recurrence kernels, sub-batches where no step passes the guard at every node: evaluated with lane = step
+    (main_sparse).  A variant build takes that path whenever it is eligible (the shipped threshold takes it when only
+    a few nodes pass); wiggler regime, SI-unit phases (flag 3), near field, snapshots."""
+    always = ('sparse_always', ('SRB_SPARSE_COST=1',))
+    tr, dt, info = cases.wiggler_tracks(3, 200)
+    args = cases.wiggler_args(info, grid=(100, 3, 2))
+    for kw in (dict(comp='cartesian', nSnaps=2), dict(comp='total'), dict(comp='spheric_complex')):
+        ref = oracle.calculate_spectrum(args, tr, dt, **kw)
+        for variant in (None, always):
+            rad, cnt = emu.run(args, tr, dt, kind='recur', variant=variant, **kw)
+            for key, r in ref['radiation'].items():
+                assert max(rel_errors(rad[key], r)) < 1e-10, (kw, variant, key)
+            assert cnt[0] == ref['passed']
+    tr, dt, info = cases.betatron_tracks(3, seed=0)
+    args = cases.betatron_args(info, grid=(100, 3, 2))
+    ref = oracle.calculate_spectrum(args, tr, dt, comp='cartesian')
+    for variant in (None, always):
+        rad, cnt = emu.run(args, tr, dt, kind='recur', comp='cartesian', variant=variant)
+        for key, r in ref['radiation'].items():
+            assert max(rel_errors(rad[key], r)) < 1e-11, (variant, key)
+        assert cnt[0] == ref['passed']
+    tr, dt, info = cases.undulator_tracks(1, near=True)
+    args = cases.undulator_args(info, near=True, grid=(64, 4, 2), L_scr=2.0)
+    args['grid'][0] = (1.0, 400.0)          # high frequencies: the guard cuts the upper nodes
+    ref = oracle.calculate_spectrum(args, tr, dt, L_screen=2.0)
+    for variant in (None, always):
+        rad, cnt = emu.run(args, tr, dt, kind='recur', L_screen=2.0, variant=variant)
+        assert max(rel_errors(rad['total'], ref['radiation']['total'])) < 1e-10, variant
+        assert cnt[0] == ref['passed']
