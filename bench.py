@@ -490,6 +490,18 @@ def run_product(a):
         'hbm_algorithmic_bytes_per_launch': nbytes_tracks,
         'hbm_gbs_algorithmic': nbytes_tracks / (k_ms * 1e-3) / 1e9,
     }
+    # HBM side, for completeness (the path is FP64-pipe bound): against the driver-measured copy bandwidth
+    try:
+        mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        roofline['hbm_peak_gbs'] = mp['hbm_gbs']
+        roofline['hbm_peak_source'] = 'MEASURED_PEAKS.json (driver-written copy bandwidth)'
+    except Exception:
+        roofline['hbm_peak_gbs'] = 7700.0
+        roofline['hbm_peak_source'] = 'B200_PROFILING.md fallback (no MEASURED_PEAKS.json)'
+    roofline['hbm_frac_algorithmic'] = roofline['hbm_gbs_algorithmic'] / roofline['hbm_peak_gbs']
+    if ev:
+        roofline['hbm_gbs_traffic'] = ev['dram_bytes_per_launch'] / (k_ms * 1e-3) / 1e9
+        roofline['hbm_frac_traffic'] = roofline['hbm_gbs_traffic'] / roofline['hbm_peak_gbs']
     line = {
         'metric': METRIC, 'value': value, 'unit': 'updates/s', 'n_gpus': world, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',

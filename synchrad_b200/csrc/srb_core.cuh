@@ -616,23 +616,23 @@ SRB_HD void prep_store(const Params& P, const Geom& g, const PrepStep& ps, int c
 // step's phasor at the reference's rounded phase (sincos_big of fl(w_j*tau): exact at any magnitude, so SI-unit
 // phases need no special case) times its amplitude, the warp sums the 2 NV products, and the node's two owner
 // lanes (cos part, sin part of tile j % 16) take them.  ~100 instructions per node instead of ~80 per step.
-// decision thresholds: instructions per node of the lane = step evaluation relative to the model of the lane = tile
-// partial loop below, for steps with huge phases (per-node sincos in both forms) and ordinary ones (recurrence in the
-// lane = tile form); measured on the C3 / C4 recipes (profiles/r02_guard_dominated.md)
-#ifndef SRB_SPARSE_COST_BIG
-#define SRB_SPARSE_COST_BIG 60
+// Which steps of a sub-batch go through main_sparse: a cost model in instructions per warp, minimised over the split
+// threshold H (steps with at most H passing nodes -> lane = step, the others -> lane = tile):
+//   lane = step : SRB_SPARSE_ROW per node row (up to the largest pass bound among its steps) + a fixed part;
+//   lane = tile : per step 50 + 40 per node row of 16 for steps with huge phases (per-node sincos), 30 + 6 for ordinary
+//                 ones (recurrence), + the seeds / records of the prep phase once.
+// Measured on the C3 / C4 recipes (profiles/r02_guard_dominated.md).
+#ifndef SRB_SPARSE_ROW
+#define SRB_SPARSE_ROW 85
 #endif
-#ifndef SRB_SPARSE_COST_SMALL
-#define SRB_SPARSE_COST_SMALL 400    // (C4 recipe: the recurrence form of the lane = tile loop is hard to beat)
-#endif
-#ifndef SRB_SPARSE_HMAX
-#define SRB_SPARSE_HMAX 8            // steps with at most this many passing nodes may be split off a mixed sub-batch
-#endif
-SRB_HD bool sparse_pays(uint32_t maxHi, uint32_t nAny, bool big) {
-  const uint32_t kmax = (maxHi + 15u) / 16u;
-  const uint32_t dense = nAny * (50u + (big ? 40u : 8u) * kmax);
-  return maxHi * (uint32_t)(big ? SRB_SPARSE_COST_BIG : SRB_SPARSE_COST_SMALL) + 64u < dense;
+SRB_HD uint32_t dense_step_cost(uint32_t flag, uint32_t hi) {
+  if (!flag) return 0u;
+  const uint32_t rows = (hi + 15u) / 16u;
+  return flag == 3u ? 50u + 40u * rows : 30u + 6u * rows;
 }
+constexpr uint32_t SPARSE_FIXED = 64u, DENSE_FIXED = 150u;
+constexpr int SPARSE_NH = 8;
+SRB_HD uint32_t sparse_threshold(int i) { return i < 7 ? (2u << i) : 0x3ffu; }     // H = 2, 4, ..., 128, everything
 #if defined(__CUDA_ARCH__)
 template <class C>
 SRB_HD void main_sparse(const Params& P, const Geom& g, const PrepStep& ps, uint32_t hi, uint32_t maxHi, int lane,
@@ -1191,15 +1191,14 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
         }
 #endif
         uint32_t fullMask = 0u, anyMask = 0u;   // bit s: step s of the sub-batch is all-pass / has any pass
-        // recurrence kernels: steps where only a few low nodes pass (hi <= SRB_SPARSE_HMAX), or the whole sub-batch when
-        // no step passes everywhere and it is cheaper, go through the lane = step evaluation (main_sparse); the others
-        // through seeds + shared-memory records + the lane = tile main phase
+        // recurrence kernels: the steps where only a few low nodes pass go through the lane = step evaluation
+        // (main_sparse), the others through seeds + shared-memory records + the lane = tile main phase; the split is
+        // chosen per sub-batch from a cost model (sparse_threshold, dense_step_cost)
         uint32_t sparseMask = 0u, maxHi = 0u;
 #if defined(__CUDA_ARCH__)
         PrepStep psv[1];
 #else
         PrepStep psv[32];
-        uint32_t bigMask = 0u;
 #endif
         SRB_LANES_BEGIN
 #if defined(__CUDA_ARCH__)
@@ -1212,27 +1211,25 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
           fullMask = __ballot_sync(0xffffffffu, ps.flag == 1u);
           anyMask = __ballot_sync(0xffffffffu, ps.flag != 0u);
           if constexpr (C::KIND == KIND_RECUR) {
-            if (anyMask != fullMask) {
-              const uint32_t bigMask = __ballot_sync(0xffffffffu, ps.flag == 3u);
-              const bool small = ps.flag != 0u && ps.hi <= (uint32_t)SRB_SPARSE_HMAX;
-              const uint32_t smallMask = __ballot_sync(0xffffffffu, small);
-              if (fullMask == 0u && (bigMask & anyMask) == 0u) {     // (ordinary phases: the whole sub-batch or nothing)
-                const uint32_t mh = __reduce_max_sync(0xffffffffu, ps.flag ? ps.hi : 0u);
-                if (sparse_pays(mh, (uint32_t)__popc(anyMask), false)) { sparseMask = anyMask; maxHi = mh; }
-              } else if (fullMask == 0u) {
-                const uint32_t mh = __reduce_max_sync(0xffffffffu, ps.flag ? ps.hi : 0u);
-                if (sparse_pays(mh, (uint32_t)__popc(anyMask), true)) { sparseMask = anyMask; maxHi = mh; }
-              }
-              if (!sparseMask && smallMask && (bigMask & smallMask)) {
+            // steps with huge phases (per-node sincos in either form) that pass at some nodes only: which form for which?
+            // (ordinary phases: the recurrence form of the lane = tile loop is not beaten, measured on the C4 recipe)
+            if (anyMask != fullMask && __ballot_sync(0xffffffffu, ps.flag == 3u)) {
+              const uint32_t mine = dense_step_cost(ps.flag, ps.hi);
+              uint32_t best = __reduce_add_sync(0xffffffffu, mine) + DENSE_FIXED;      // everything lane = tile
+#pragma unroll
+              for (int i = 0; i < SPARSE_NH; i++) {
+                const bool small = ps.flag == 3u && ps.hi <= sparse_threshold(i);
                 const uint32_t mh = __reduce_max_sync(0xffffffffu, small ? ps.hi : 0u);
-                if (sparse_pays(mh, (uint32_t)__popc(smallMask), true)) { sparseMask = smallMask; maxHi = mh; }
+                if (mh == 0u) continue;                                                 // warp-uniform
+                const uint32_t rest = __reduce_add_sync(0xffffffffu, small ? 0u : mine);
+                const uint32_t cost = mh * (uint32_t)SRB_SPARSE_ROW + SPARSE_FIXED + (rest ? rest + DENSE_FIXED : 0u);
+                if (cost < best) { best = cost; sparseMask = __ballot_sync(0xffffffffu, small); maxHi = mh; }
               }
             }
           }
 #else
           if (ps.flag == 1u) fullMask |= 1u << lane;
           if (ps.flag != 0u) anyMask |= 1u << lane;
-          if (ps.flag == 3u) bigMask |= 1u << lane;
 #endif
         SRB_LANES_END
 #if defined(SRB_SKIP_MAIN)      // tuning aid: the cost of the guard part of the prep phase alone
@@ -1240,14 +1237,20 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
 #endif
 #if !defined(__CUDA_ARCH__)
         if (C::KIND == KIND_RECUR && anyMask != fullMask) {      // the same decision, lanes as a loop
-          uint32_t smallMask = 0u, mhAll = 0u, mhSmall = 0u;
-          for (int l = 0; l < 32; l++) {
-            if (!psv[l].flag) continue;
-            if (psv[l].hi > mhAll) mhAll = psv[l].hi;
-            if (psv[l].hi <= (uint32_t)SRB_SPARSE_HMAX) { smallMask |= 1u << l; if (psv[l].hi > mhSmall) mhSmall = psv[l].hi; }
+          uint32_t all = 0u;
+          for (int l = 0; l < 32; l++) all += dense_step_cost(psv[l].flag, psv[l].hi);
+          uint32_t best = all + DENSE_FIXED;
+          for (int i = 0; i < SPARSE_NH; i++) {
+            uint32_t mh = 0u, rest = 0u, mask = 0u;
+            for (int l = 0; l < 32; l++) {
+              const bool small = psv[l].flag == 3u && psv[l].hi <= sparse_threshold(i);
+              if (small) { mask |= 1u << l; if (psv[l].hi > mh) mh = psv[l].hi; }
+              else rest += dense_step_cost(psv[l].flag, psv[l].hi);
+            }
+            if (mh == 0u) continue;
+            const uint32_t cost = mh * (uint32_t)SRB_SPARSE_ROW + SPARSE_FIXED + (rest ? rest + DENSE_FIXED : 0u);
+            if (cost < best) { best = cost; sparseMask = mask; maxHi = mh; }
           }
-          if (fullMask == 0u && sparse_pays(mhAll, (uint32_t)__builtin_popcount(anyMask), (bigMask & anyMask) != 0u)) { sparseMask = anyMask; maxHi = mhAll; }
-          if (!sparseMask && smallMask && (bigMask & smallMask) && sparse_pays(mhSmall, (uint32_t)__builtin_popcount(smallMask), true)) { sparseMask = smallMask; maxHi = mhSmall; }
         }
 #endif
         if constexpr (C::KIND == KIND_RECUR) {

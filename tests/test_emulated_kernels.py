@@ -273,7 +273,7 @@ def test_guard_dominated_sub_batches_lane_is_step(oracle):
     """Recurrence kernels, sub-batches where no step passes the guard at every node: evaluated with lane = step
     (main_sparse).  A variant build takes that path whenever it is eligible (the shipped threshold takes it when only
     a few nodes pass); wiggler regime, SI-unit phases (flag 3), near field, snapshots."""
-    always = ('sparse_always', ('SRB_SPARSE_COST=1',))
+    always = ('sparse_always', ('SRB_SPARSE_ROW=1',))
     tr, dt, info = cases.wiggler_tracks(3, 200)
     args = cases.wiggler_args(info, grid=(100, 3, 2))
     for kw in (dict(comp='cartesian', nSnaps=2), dict(comp='total'), dict(comp='spheric_complex')):
