@@ -3,6 +3,7 @@ mkdir -p gpurun_out
 T=${1:-a}
 timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/freeze_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/freeze_pytest_gpu.txt
 timeout 900 python bench.py > gpurun_out/bench_r02_freeze_$T.json 2> gpurun_out/bench_r02_freeze_$T.err; echo "bench rc=$?"
+python -c "import bench; print(bench.csrc_hash())" > gpurun_out/headline_csrc_sha.txt
 M=$(python tools/ncu_headline.py --metrics)
 timeout 900 ncu --clock-control none -k regex:k_integrate_ws -s 1 -c 1 --csv --metrics $M --log-file gpurun_out/headline_metrics.csv python tools/quick_perf.py 12500 10000 double auto 1 > gpurun_out/ncu_headline.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate_ws -s 1 -c 1 -f -o gpurun_out/prof_r02_ws_final python tools/quick_perf.py 592 2000 double auto 1 > gpurun_out/ncu_ws_final.log 2>&1

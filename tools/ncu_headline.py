@@ -4,7 +4,8 @@ On the GPU box (tools/gpu_job_headline_ncu.sh):
     ncu --clock-control none -k regex:k_integrate -s 1 -c 1 --csv --metrics <METRICS> --log-file gpurun_out/headline_metrics.csv \
         python tools/quick_perf.py 12500 10000 double auto 1
 here:
-    python tools/ncu_headline.py gpurun_out/headline_metrics.csv 12500 10000
+    python tools/ncu_headline.py gpurun_out/headline_metrics.csv 12500 10000 gpurun_out/headline_csrc_sha.txt
+(the last file holds bench.csrc_hash() of the sources the capture ran, written by the same job)
 
 bench.py reports `roofline.traffic` and the pipe-busy fractions from this file only when its `csrc_sha` equals the hash
 of the sources the benchmark runs (bench.csrc_hash) and kernel / shard match; otherwise it prints None and says why."""
@@ -24,6 +25,7 @@ def main():
     if len(sys.argv) == 2 and sys.argv[1] == '--metrics':
         print(METRICS); return
     path, n_p, n_s = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    sha = open(sys.argv[4]).read().strip()          # hash of the sources the capture ran (not of whatever is here now)
     rows = [r for r in csv.reader(open(path, errors='replace')) if len(r) >= 15 and r[0] != 'ID']
     if not rows:
         sys.exit('no metric rows in ' + path)
@@ -36,7 +38,7 @@ def main():
     info = I(); info.kind, info.tile_width, info.n_components = kind, tw, nc
     grid, block = rows[0][8], rows[0][7]
     rec = {
-        'csrc_sha': bench.csrc_hash(), 'kernel': bench.kernel_label(info, fp64, kind), 'ncu_kernel_name': name,
+        'csrc_sha': sha, 'kernel': bench.kernel_label(info, fp64, kind), 'ncu_kernel_name': name,
         'warp_specialised': 'k_integrate_ws' in name,
         'particles': n_p, 'track_steps': n_s, 'grid': grid, 'block': block,
         'command': f'ncu --clock-control none -k regex:k_integrate -s 1 -c 1 --metrics ... python tools/quick_perf.py {n_p} {n_s} double auto 1',
