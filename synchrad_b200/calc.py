@@ -285,6 +285,8 @@ class SynchRad(Utilities):
             from .dist import reduce_to_root
             dev_out, self.total_weight, cnt = reduce_to_root(self.comm, dev_out, self.total_weight, cnt)
         self.Data['radiation'] = {k: d.cpu().numpy() for k, d in zip(keys, dev_out)}
+        # calc.py:475-480 keeps the form-factor table in Data as well (there a device array; here the host table)
+        self.Data['FormFactor'] = host.form_factor(self.Args)
         # the summed result stays on the device of rank 0 for the on-device post-processing (utils.py, on_device=True)
         self._dev_radiation = dict(zip(keys, dev_out)) if self.rank == 0 else None
         c = cnt.cpu().numpy()

@@ -155,6 +155,34 @@ def test_c3_betatron_recipe_si_units(cuda_lib, oracle):
     assert_close(coh, oracle.calculate_spectrum(args, tracks, dt, comp='cartesian_complex')['radiation'], tol=1e-9)
 
 
+def test_c2_near_full_grid_all_phi_planes(cuda_lib, oracle):
+    """configs[1] at its full size (128x256x32, all 32 phi planes, omega*(t+R) ~ 1e10 rad) against the strict oracle:
+    the corrected-recurrence kernel at the size its 1e-9 claim is made for (~10 s of oracle on the box's cores)."""
+    tracks, dt, info = cases.undulator_tracks(1, near=True)
+    args = cases.undulator_args(info, near=True)
+    calc = run_gpu(args, tracks, dt, L_screen=1e5)
+    ref = oracle.calculate_spectrum(args, tracks, dt, L_screen=1e5)
+    assert_close(calc, ref['radiation'])
+    assert calc.last_run['kernel'] == 'drec'
+    assert calc.last_run['passed_updates'] == ref['passed']
+    assert calc.last_run['updates'] == ref['updates'] == 3328 * 128 * 256 * 32
+
+
+def test_c3_recipe_full_size(cuda_lib, oracle):
+    """configs[2] at its full size: 10^3 betatron electrons (SI units), 256x32x32, cartesian -- 37 particle chunks whose
+    private partial spectra are reduced in fixed order, guard-dominated sub-batches through the lane = step path."""
+    tracks, dt, info = cases.betatron_tracks(1000, seed=0)
+    args = cases.betatron_args(info)
+    calc = run_gpu(args, tracks, dt, comp='cartesian')
+    ref = oracle.calculate_spectrum(args, tracks, dt, comp='cartesian')
+    assert_close(calc, ref['radiation'], tol=1e-10)
+    assert calc.last_run['kernel'] == 'recurrence' and calc.last_run['particle_chunks'] > 8
+    assert calc.last_run['passed_updates'] == ref['passed']
+    again = run_gpu(args, tracks, dt, comp='cartesian')               # bit-reproducible
+    for k in ref['radiation']:
+        assert np.array_equal(again.Data['radiation'][k], calc.Data['radiation'][k])
+
+
 def test_c3_like_si_units(cuda_lib, oracle):
     tracks, dt, info = cases.wiggler_tracks(8, 256, si_scale=1e-3)
     args = cases.wiggler_args(info, grid=(256, 8, 4), si_scale=1e-3)
