@@ -58,9 +58,11 @@ extern "C" {
 #define SRB_DTYPE_F32_LITERAL 2
 
 /* phasor: how exp(i*omega*tau) is evaluated per node */
-#define SRB_PHASOR_AUTO 0   /* uniform grid: pair kernel (far field) or recurrence, chosen ON THE DEVICE from a sampled
-                               Nyquist-guard statistic (both are enqueued, the other returns at once; no host
-                               synchronisation; choice reported in counters[2]); else direct */
+#define SRB_PHASOR_AUTO 0   /* uniform grid, far field: pair kernel, recurrence (many partially passing steps) or -- fp64,
+                               mostly all-pass steps with phases beyond 2^18 -- corrected recurrence, chosen ON THE DEVICE
+                               from a sampled Nyquist-guard / phase statistic (all candidates are enqueued, the others
+                               return at once; no host synchronisation; choice reported in counters[2]); near field:
+                               recurrence or corrected recurrence by omega*L; non-uniform grids: direct */
 #define SRB_PHASOR_DIRECT 1 /* per-node sincos of the reference's rounded phase */
 #define SRB_PHASOR_RECUR 2  /* three-term recurrence along omega (uniform grids only) */
 #define SRB_PHASOR_PAIR 3   /* symmetric node pairs about the tile centre, broadcast pair phasors (uniform grids, far

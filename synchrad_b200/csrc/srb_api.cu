@@ -403,16 +403,24 @@ __global__ void k_probe(const srb::Params P, uint64_t total, double wFirst, doub
   const double* x = (const double*)P.x; const double* y = (const double*)P.y; const double* z = (const double*)P.z;
   const double dtau = fabs(P.dt - ((x[gs] - x[gs - 1]) * sT * cP + (y[gs] - y[gs - 1]) * sT * sP + (z[gs] - z[gs - 1]) * cT));
   atomicAdd(out, 1u);
+  bool some = true;
   if (wLast * dtau < 3.14159265358979323846) atomicAdd(out + 1, 1u);
   else if (wFirst * dtau < 3.14159265358979323846) atomicAdd(out + 2, 1u);
+  else some = false;
+  // passing steps whose phase at the last node is beyond the 2^18 limit of the phase-tracking kernels (SI-unit tracks)
+  const double tau = (double)(P.itStart[a] + (uint32_t)it) * P.dt - (x[gs] * sT * cP + y[gs] * sT * sP + z[gs] * cT);
+  if (some && fabs(wLast * tau) > 262144.0) atomicAdd(out + 3, 1u);
 }
 
 // phasor = AUTO: the decision from the probe counts, on the device (no host round trip): partial steps cost the pair
 // kernel ~3x, so it is taken only when they are < 10 % of the all-pass ones.  sel[0] = chosen kind; the same code is
 // left in counters[2] for the caller.
-__global__ void k_decide(const unsigned int* probe, int32_t* sel, unsigned long long* counters) {
+__global__ void k_decide(const unsigned int* probe, int32_t* sel, unsigned long long* counters, int haveDrec) {
   const bool preferRecur = probe[0] > 0 && (double)probe[2] > 0.1 * (double)probe[1];
-  sel[0] = preferRecur ? srb::KIND_RECUR : srb::KIND_PAIR;
+  // mostly all-pass steps with huge phases (SI-unit tracks): neither phase-tracking kernel applies (every step would be
+  // evaluated node by node), the corrected-recurrence kernel does (srb_drec.cuh)
+  const bool big = haveDrec && 2.0 * (double)probe[3] > (double)probe[1] + (double)probe[2];
+  sel[0] = preferRecur ? srb::KIND_RECUR : (big ? srb::KIND_DREC : srb::KIND_PAIR);
   if (counters) counters[2] = (unsigned long long)sel[0];
 }
 
@@ -633,7 +641,7 @@ int validate(const srb_grid* g, const srb_tracks* t) {
 }
 
 int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool unlimited, Plan* p,
-              bool preferRecur = false) {
+              bool preferRecur = false, bool forceDrec = false) {
   int dev = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&p->numSM, cudaDevAttrMultiProcessorCount, dev));
@@ -655,6 +663,7 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
     if (!uniform || g->dtype != SRB_DTYPE_F64) return fail("the corrected-recurrence kernel needs fp64 and an ascending uniform omega grid");
     p->kind = KIND_DREC;
   }
+  if (forceDrec && uniform && g->dtype == SRB_DTYPE_F64) p->kind = KIND_DREC;     // third candidate of phasor = AUTO (far field)
   if (g->dtype == SRB_DTYPE_F32_LITERAL) p->kind = KIND_LITERAL;
   p->native = (p->kind == KIND_DIRECT && g->dtype == SRB_DTYPE_F32 && g->native != 0);   // Q9
   const int tiles = p->kind == KIND_RECUR ? 16 : 32;
@@ -796,7 +805,12 @@ size_t srb_scratch_bytes(const srb_grid* grid, const srb_tracks* tracks) {
   if (make_plan(grid, tracks, 0, true, &q, true) != 0) return 0;
   const size_t a = (p.work_doubles() + p.preDoubles) * sizeof(double);
   const size_t b = (q.work_doubles() + q.preDoubles) * sizeof(double);
-  return 64 + std::max(a, b);        // 64-byte header: guard probe counts + on-device kernel choice (phasor = AUTO)
+  size_t c = 0;
+  if (grid->dtype == SRB_DTYPE_F64 && grid->mode == SRB_MODE_FAR && grid->phasor == SRB_PHASOR_AUTO) {
+    Plan r;
+    if (make_plan(grid, tracks, 0, true, &r, false, true) == 0) c = (r.work_doubles() + r.preDoubles) * sizeof(double);
+  }
+  return 64 + std::max(std::max(a, b), c);        // 64-byte header: guard probe counts + on-device kernel choice (phasor = AUTO)
 }
 
 // one plan's launches: [pre-pass] [zero the private partial spectra] kernel [reduce]; `sel`/`want`: see Params::sel
@@ -894,16 +908,21 @@ int srb_integrate(const srb_grid* g, const srb_tracks* t, double* const* spectra
       srb::Params Q;
       std::memset(&Q, 0, sizeof Q);
       Q.nA2 = g->nAxis2; Q.nPhi = g->nPhi; Q.axA = g->sinTheta; Q.axB = g->cosTheta; Q.sinPhi = g->sinPhi; Q.cosPhi = g->cosPhi;
-      Q.dt = g->dt; Q.nTracks = t->nTracks; Q.x = t->x; Q.y = t->y; Q.z = t->z; Q.offsets = t->offsets;
+      Q.dt = g->dt; Q.nTracks = t->nTracks; Q.x = t->x; Q.y = t->y; Q.z = t->z; Q.offsets = t->offsets; Q.itStart = t->itStart;
+      // third candidate (fp64): the corrected-recurrence kernel, for mostly all-pass steps with phases beyond 2^18
+      Plan pDrec;
+      const bool haveDrec = g->dtype == SRB_DTYPE_F64 && make_plan(g, t, scratch_bytes - 64, false, &pDrec, false, true) == 0 &&
+                            pDrec.kind == KIND_DREC;
       SRB_CUDA(cudaMemsetAsync(probeBuf, 0, 64, stream));
       k_probe<<<64, 128, 0, stream>>>(Q, t->totalSteps_host, g->omega_first_host, g->omega_last_host, probeBuf);
-      k_decide<<<1, 1, 0, stream>>>(probeBuf, sel, (unsigned long long*)counters);
+      k_decide<<<1, 1, 0, stream>>>(probeBuf, sel, (unsigned long long*)counters, haveDrec ? 1 : 0);
       SRB_CUDA(cudaGetLastError());
       launched += 2;
-      // the two candidates share the scratch body (only one of them runs): zero both slab regions first, then the
-      // (conditional) pre-passes, kernels and reductions
+      // the candidates share the scratch body (only one of them runs): each one's launch sequence clears its own work
+      // area, then the (conditional) pre-pass, kernel and reduction
       if (launch_plan(g, t, pPair, spectra, body, counters, stream, sel, pPair.kind, &launched) != 0) return -1;
       if (launch_plan(g, t, pRec, spectra, body, counters, stream, sel, pRec.kind, &launched) != 0) return -1;
+      if (haveDrec && launch_plan(g, t, pDrec, spectra, body, counters, stream, sel, pDrec.kind, &launched) != 0) return -1;
       fill_info(pPair, launched, SRB_KIND_ON_DEVICE);
       return 0;
     }

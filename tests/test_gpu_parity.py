@@ -183,6 +183,25 @@ def test_c3_recipe_full_size(cuda_lib, oracle):
         assert np.array_equal(again.Data['radiation'][k], calc.Data['radiation'][k])
 
 
+def test_auto_takes_corrected_recurrence_for_all_pass_steps_with_huge_phases(cuda_lib, oracle):
+    """Far field, guard-pass dominated, phases beyond 2^18 (here: the undulator electron 10 length units downstream of the
+    origin, omega*n.r ~ 1.4e6 rad): neither phase-tracking kernel applies; the device-side probe sends phasor='auto' to
+    the corrected-recurrence kernel (third candidate), fp32 keeps the pair kernel (fp64 seeds, no such limit)."""
+    tracks, dt, info = cases.undulator_tracks(2, seed=3)
+    tracks = [[t[0], t[1], t[2] + 10.0] + list(t[3:]) for t in tracks]
+    args = cases.undulator_args(info, grid=(128, 8, 8))
+    for comp in ('total', 'cartesian_complex'):
+        ref = oracle.calculate_spectrum(args, tracks, dt, comp=comp)
+        calc = run_gpu(args, tracks, dt, comp=comp)
+        assert calc.last_run['kernel'] == 'drec', calc.last_run
+        assert_close(calc, ref['radiation'], what=comp)
+        assert calc.last_run['passed_updates'] == ref['passed']
+        for phasor in ('pair', 'recur'):                  # the explicit choices stay correct (node by node), only slower
+            assert_close(run_gpu(args, tracks, dt, phasor=phasor, comp=comp), ref['radiation'], what=(comp, phasor))
+    a32 = cases.undulator_args(info, grid=(128, 8, 8), dtype='float')
+    assert run_gpu(a32, tracks, dt).last_run['kernel'] == 'pair'
+
+
 def test_c3_like_si_units(cuda_lib, oracle):
     tracks, dt, info = cases.wiggler_tracks(8, 256, si_scale=1e-3)
     args = cases.wiggler_args(info, grid=(256, 8, 4), si_scale=1e-3)
@@ -553,8 +572,9 @@ def test_scratch_size_only_changes_parallelism(cuda_lib):
 
 
 def test_auto_choice_is_made_on_the_device(cuda_lib, oracle):
-    """phasor='auto' with both uniform-grid kernels eligible: a probe kernel samples the guard statistics, the choice
-    is made on the device (both candidates enqueued, one returns at once) -- srb_integrate never synchronises the
+    """phasor='auto' with several uniform-grid kernels eligible (fp64 far field: pair, recurrence, corrected recurrence):
+    a probe kernel samples the guard / phase statistics, the choice is made on the device (all candidates enqueued, the
+    ones not chosen return at once) -- srb_integrate never synchronises the
     stream; the choice is reported through counters[2]."""
     import torch
     from synchrad_b200 import engine, host
@@ -568,7 +588,7 @@ def test_auto_choice_is_made_on_the_device(cuda_lib, oracle):
         pk = host.pack_tracks(tracks, [t[6] for t in tracks], np.double, None, 1)
         res = engine.integrate(args, dtype, grid, pk, 'total', 1, phasor='auto')
         assert int(res.info.kind) == -1 and res.kind == want          # SRB_KIND_ON_DEVICE; all-pass -> pair, guard-dominated -> recurrence
-        assert res.info.kernels_launched == 8                         # probe, decide, 2 x (pre-pass, integrate, reduce)
+        assert res.info.kernels_launched == 11                        # probe, decide, 3 candidates x (pre-pass, integrate, reduce)
         ref = oracle.calculate_spectrum(a, tracks, dt)
         got = np.ascontiguousarray(res.spectra[0].cpu().numpy().swapaxes(-1, -3))
         assert max(rel_errors(got, ref['radiation']['total'])) < 1e-9

@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 500 -k "full_grid_all_phi or c3_recipe_full" 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 500 2>&1 | tail -15
+timeout 100 python tools/quick_perf.py 592 10000 double auto 2 2>/dev/null | tail -1
