@@ -304,7 +304,8 @@ struct Cfg {
   static constexpr int NREC = KIND_ == KIND_LITERAL ? (MODE_ == MODE_FAR ? 4 : 8)
       : PAIR ? (NREC_PAIR > NREC_FLUSH ? NREC_PAIR : NREC_FLUSH)
       : KIND_ == KIND_DREC ? ((NV + 5 + 1) & ~1)   // V[NV], tau, R^32 (Re, Im), conj-rotated... see srb_drec.cuh: tau, wr, wi, 2cos, pad
-      : (((NV + (KIND_ == KIND_RECUR ? 3 : (sizeof(TM_) == 4 ? 2 : 1))) + 1) & ~1);   // direct, fp32: tau as hi + lo
+      : KIND_ == KIND_RECUR ? (sizeof(TM_) == 4 ? ((NV + 3 + 3) & ~3) : ((NV + 3 + 1) & ~1))   // 16-byte rows: rec_row() reads them with 128-bit loads
+      : (((NV + (sizeof(TM_) == 4 ? 2 : 1)) + 1) & ~1);   // direct, fp32: tau as hi + lo
   static constexpr bool DIRECTLIKE = KIND_ == KIND_DIRECT || KIND_ == KIND_DREC;         // lane = tile {lane + 32k}, Re and Im per node
   using TW_T = typename std::conditional<DIRECTLIKE, double, TM_>::type;                 // type of the lane's omega nodes
 };
@@ -316,7 +317,7 @@ template <bool ON> struct DrecSmem {};
 template <> struct alignas(16) DrecSmem<true> { Cpx seed[SUB][13]; };
 
 template <class C>
-struct WarpSmem : DrecSmem<C::KIND == KIND_DREC> {
+struct alignas(16) WarpSmem : DrecSmem<C::KIND == KIND_DREC> {
   typename C::TM rec[SUB][C::NREC];       // per-step record (see Cfg::NREC)
   uint32_t rng[SUB];                      // lo | hi<<10 | flag<<30 (chunk-relative pass range)
   typename C::TM seeds[C::NSEED][SUB + 1];  // [part*16+tile][step]: cos|sin of the tile's first node
@@ -726,6 +727,38 @@ SRB_HD int low_bit(uint32_t m) {
 // smallest tile-local index k with m + T*k >= j (chunk-relative node bound j >= 0): ceil((j-m)/T)
 SRB_HD int tile_lo(int j, int m, int T) { const int d = j - m; return d <= 0 ? 0 : (d + T - 1) / T; }
 
+// the NV + 3 entries of a recurrence-kernel record (V, 2cos(d) | tau, cos(d), sin(d)) with 128-bit shared-memory loads
+template <class C>
+SRB_HD void rec_row(const WarpSmem<C>& sm, int s, typename C::TM* R) {
+  using TM = typename C::TM;
+  constexpr int N = C::NV + 3;
+#if defined(__CUDA_ARCH__)
+  if constexpr (sizeof(TM) == 4 && C::NREC % 4 == 0) {
+    const float4* q = reinterpret_cast<const float4*>(&sm.rec[s][0]);
+#pragma unroll
+    for (int i = 0; i < (N + 3) / 4; i++) {
+      const float4 t = q[i];
+      if (4 * i + 0 < N) R[4 * i + 0] = t.x;
+      if (4 * i + 1 < N) R[4 * i + 1] = t.y;
+      if (4 * i + 2 < N) R[4 * i + 2] = t.z;
+      if (4 * i + 3 < N) R[4 * i + 3] = t.w;
+    }
+    return;
+  } else if constexpr (sizeof(TM) == 8 && C::NREC % 2 == 0) {
+    const double2* q = reinterpret_cast<const double2*>(&sm.rec[s][0]);
+#pragma unroll
+    for (int i = 0; i < (N + 1) / 2; i++) {
+      const double2 t = q[i];
+      if (2 * i + 0 < N) R[2 * i + 0] = t.x;
+      if (2 * i + 1 < N) R[2 * i + 1] = t.y;
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int k = 0; k < N; k++) R[k] = sm.rec[s][k];
+}
+
 // one full step of one tile: v0, v1 = first two nodes of the tile, then the three-term recurrence
 template <class C>
 SRB_HD void tile_step_full(const typename C::TM* V, typename C::TM coef, typename C::TM vm, typename C::TM v,
@@ -758,14 +791,12 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     // hot path: every step of the sub-batch passes the guard at every node of the chunk.
     // Operands of step s+1 are fetched from shared memory while step s is being accumulated.
     TM R[NV + 3], nR[NV + 3], x, xo, nx, nxo;
-#pragma unroll
-    for (int k = 0; k < NV + 3; k++) R[k] = sm.rec[0][k];
+    rec_row<C>(sm, 0, R);
     x = sm.seeds[lane][0]; xo = sm.seeds[lane ^ 16][0];
 #pragma unroll 2
     for (int s = 0; s < cnt; s++) {
       const int sn = s + 1 < cnt ? s + 1 : s;
-#pragma unroll
-      for (int k = 0; k < NV + 3; k++) nR[k] = sm.rec[sn][k];
+      rec_row<C>(sm, sn, nR);
       nx = sm.seeds[lane][sn]; nxo = sm.seeds[lane ^ 16][sn];
       // second node of the tile: cos lane c1 = c0*cd - s0*sd ; sin lane s1 = s0*cd + c0*sd
       const TM v1 = fma(xo, flipsign(R[NV + 2], sgn), x * R[NV + 1]);
@@ -780,12 +811,13 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
     const int s = low_bit(todo);
     const uint32_t r = sm.rng[s];
     const uint32_t flag = r >> 30;
-    TM V[NV];
-#pragma unroll
-    for (int k = 0; k < NV; k++) V[k] = sm.rec[s][k];
-    const TM coef = sm.rec[s][NV];
-    // tile-local k passes iff lo <= m + 16k < hi ; kmax = largest count over the tiles (tile 0), uniform
-    const int lo = tile_lo((int)(r & 0x3ffu), m, 16), hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
+    TM V[NV + 3];                         // V, 2cos(d) (flag 3: tau), cos(d), sin(d)
+    rec_row<C>(sm, s, V);
+    const TM coef = V[NV];
+    // tile-local k passes iff m + 16k < hi (ascending uniform grid: the pass range starts at node 0) ;
+    // kmax = largest count over the tiles (tile 0), uniform
+    constexpr int lo = 0;
+    const int hi = tile_lo((int)((r >> 10) & 0x3ffu), m, 16);
     const int kmax = tile_lo((int)((r >> 10) & 0x3ffu), 0, 16);
     if (flag == 3) {   // direct evaluation of this step (phase too large for the recurrence)
       const uint32_t j0 = g.cLo + (uint32_t)m;
@@ -810,7 +842,7 @@ SRB_HD void main_recur(const Params& P, const Geom& g, const WarpSmem<C>& sm, in
       continue;
     }
     TM vm = sm.seeds[lane][s];
-    TM v = fma(sm.seeds[lane ^ 16][s], flipsign(sm.rec[s][NV + 2], sgn), vm * sm.rec[s][NV + 1]);
+    TM v = fma(sm.seeds[lane ^ 16][s], flipsign(V[NV + 2], sgn), vm * V[NV + 1]);
     if (flag == 1) {
       tile_step_full<C>(V, coef, vm, v, st);
     } else {
