@@ -980,68 +980,113 @@ SRB_HD void emit_node(const Params& P, const Geom& g, double w, uint32_t pc, siz
 // Split layout (recurrence kernels): lanes l and l^16 hold the cos and sin parts of the same 16
 // tiles, so the partner's accumulators of node k are fetched (GPU: shuffles; emulator: direct
 // read) and both lanes reconstruct the full complex amplitude; lane part 0 then writes.
+// one node of the flush: ma = this lane's NPN accumulators of tile-local node k, pa = the partner lane's (split layout
+// of the recurrence kernels only)
 template <class C>
-SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint32_t pc, uint32_t iSnap,
-                       int lane, const ThreadState<C>* st) {
+SRB_HD void flush_node(const Params& P, const Geom& g, const TrackView& tv, uint32_t pc, uint32_t iSnap, int lane, int k,
+                       const double* ma, const double* pa) {
   using TI = typename C::TI;
-  constexpr int TW = C::TW;
   constexpr int NPN = C::NPN;
   constexpr int NCF = (C::MODE == MODE_FAR) ? C::NC : 3;   // complex amplitude components held
-#if defined(__CUDA_ARCH__)
-  const ThreadState<C>& me = st[0];
-#else
-  const ThreadState<C>& me = st[lane];
-#endif
   const size_t nTotal = (size_t)P.nOmega * P.nA2 * P.nPhi;
   const int tile = (C::KIND == KIND_RECUR) ? (lane & 15) : lane;
   const int part = (C::KIND == KIND_RECUR) ? (lane >> 4) : 0;
+  const uint32_t j = g.cLo + (uint32_t)(tile + C::TILES * k);
+  if (!(j < g.cHi)) return;
+  const size_t idx = (size_t)j + (size_t)P.nOmega * (g.iA2 + (size_t)P.nA2 * g.iPhi) + nTotal * iSnap;
+  double re[3], im[3];
+  if constexpr (C::DIRECTLIKE || C::PAIR) {
+#pragma unroll
+    for (int c = 0; c < NCF; c++) { re[c] = ma[c]; im[c] = ma[NCF + c]; }
+  } else {
+    const double* cosS = part ? pa : ma;
+    const double* sinS = part ? ma : pa;
+    if (C::MODE == MODE_FAR) {
+#pragma unroll
+      for (int c = 0; c < NCF; c++) { re[c] = cosS[c]; im[c] = sinS[c]; }
+    } else {
+      // near: acc = {P = sum B*v, Q = sum Cv*v}; Re = Qcos - w*Psin, Im = Qsin + w*Pcos
+      const double wj = (double)((const TI*)P.omega)[j];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        re[c] = cosS[(NPN > 3 ? 3 : 0) + c] - wj * sinS[c];
+        im[c] = sinS[(NPN > 3 ? 3 : 0) + c] + wj * cosS[c];
+      }
+    }
+  }
+  if (P.nTS > 1u) {   // time-axis split: this segment's partial amplitude, squared after the segments are summed
+    if (part == 0) {
+      double* a = P.amp + (((size_t)pc * P.nSnaps + iSnap) * (size_t)(2 * NCF)) * nTotal + (idx - nTotal * iSnap);
+#pragma unroll
+      for (int c = 0; c < NCF; c++) { a[(size_t)c * nTotal] = re[c]; a[(size_t)(NCF + c) * nTotal] = im[c]; }
+    }
+    return;
+  }
+  emit_node<C::MODE, NCF>(P, g, tv.w, pc, idx, j, re, im, part == 0, C::KIND != KIND_RECUR || part == 1);
+}
+
+// `stage` (GPU, non-pair kinds): the warp's idle staging area.  The accumulators go through it so that the loop over the
+// lane's nodes can stay ROLLED: unrolled over 16-node tiles the flush is ~90 KB of code, executed once per (track,
+// direction) -- on short tracks it kept evicting the hot loops from the instruction cache (C3 recipe: `no_instruction`
+// was the top stall, profiles/r02_guard_dominated.md).
+template <class C>
+SRB_HD void flush_lane(const Params& P, const Geom& g, const TrackView& tv, uint32_t pc, uint32_t iSnap,
+                       int lane, const ThreadState<C>* st, typename C::TM* stage = nullptr) {
+  using TM = typename C::TM;
+  constexpr int TW = C::TW;
+  constexpr int NPN = C::NPN;
+#if defined(__CUDA_ARCH__)
+  const ThreadState<C>& me = st[0];
+  constexpr int CAP = (int)(sizeof(WarpSmem<C>) / (32 * sizeof(TM)));     // accumulators per lane that fit
+  constexpr int KC = CAP / NPN >= TW ? TW : CAP / NPN;                     // nodes per pass (0: the direct kinds' small area)
+  if constexpr (!C::PAIR && KC >= 1) {
+    if (stage) {
+#pragma unroll
+      for (int k0 = 0; k0 < TW; k0 += KC) {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < KC * NPN; q++)
+          if (k0 * NPN + q < C::NACC) stage[q * 32 + lane] = me.acc[k0 * NPN + q];
+        __syncwarp();
+#pragma unroll 1
+        for (int kk = 0; kk < KC; kk++) {
+          if (k0 + kk >= TW) break;
+          double ma[NPN], pa[NPN];
+#pragma unroll
+          for (int c = 0; c < NPN; c++) {
+            ma[c] = (double)stage[(kk * NPN + c) * 32 + lane];
+            pa[c] = C::KIND == KIND_RECUR ? (double)stage[(kk * NPN + c) * 32 + (lane ^ 16)] : 0.0;
+          }
+          flush_node<C>(P, g, tv, pc, iSnap, lane, k0 + kk, ma, pa);
+        }
+      }
+      __syncwarp();
+      return;
+    }
+  }
+#else
+  const ThreadState<C>& me = st[lane];
+  (void)stage;
+#endif
 #pragma unroll
   for (int k = 0; k < TW; k++) {
-    const uint32_t j = g.cLo + (uint32_t)(tile + C::TILES * k);
-    const bool valid = j < g.cHi;
-    const size_t idx = (size_t)j + (size_t)P.nOmega * (g.iA2 + (size_t)P.nA2 * g.iPhi) + nTotal * iSnap;
-    double re[3], im[3];
+    double ma[NPN > 6 ? NPN : 6], pa[NPN > 6 ? NPN : 6];
     if constexpr (C::PAIR) {
-      pair_node_amp<C>(me, k, re, im);
-    } else if constexpr (C::DIRECTLIKE) {
-#pragma unroll
-      for (int c = 0; c < NCF; c++) { re[c] = (double)me.acc[k * NPN + c]; im[c] = (double)me.acc[k * NPN + NCF + c]; }
+      pair_node_amp<C>(me, k, ma, ma + ((C::MODE == MODE_FAR) ? C::NC : 3));
     } else {
-      double ma[NPN], pa[NPN];
 #pragma unroll
       for (int c = 0; c < NPN; c++) {
         ma[c] = (double)me.acc[k * NPN + c];
+        if (C::KIND == KIND_RECUR) {
 #if defined(__CUDA_ARCH__)
-        pa[c] = __shfl_xor_sync(0xffffffffu, ma[c], 16);
+          pa[c] = __shfl_xor_sync(0xffffffffu, ma[c], 16);
 #else
-        pa[c] = (double)st[lane ^ 16].acc[k * NPN + c];
+          pa[c] = (double)st[lane ^ 16].acc[k * NPN + c];
 #endif
-      }
-      const double* cosS = part ? pa : ma;
-      const double* sinS = part ? ma : pa;
-      if (C::MODE == MODE_FAR) {
-#pragma unroll
-        for (int c = 0; c < NCF; c++) { re[c] = cosS[c]; im[c] = sinS[c]; }
-      } else {
-        // near: acc = {P = sum B*v, Q = sum Cv*v}; Re = Qcos - w*Psin, Im = Qsin + w*Pcos
-        const double wj = valid ? (double)((const TI*)P.omega)[j] : 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          re[c] = cosS[(NPN > 3 ? 3 : 0) + c] - wj * sinS[c];
-          im[c] = sinS[(NPN > 3 ? 3 : 0) + c] + wj * cosS[c];
         }
       }
     }
-    if (!valid) continue;
-    if (P.nTS > 1u) {   // time-axis split: this segment's partial amplitude, squared after the segments are summed
-      if (part == 0) {
-        double* a = P.amp + (((size_t)pc * P.nSnaps + iSnap) * (size_t)(2 * NCF)) * nTotal + (idx - nTotal * iSnap);
-#pragma unroll
-        for (int c = 0; c < NCF; c++) { a[(size_t)c * nTotal] = re[c]; a[(size_t)(NCF + c) * nTotal] = im[c]; }
-      }
-      continue;
-    }
-    emit_node<C::MODE, NCF>(P, g, tv.w, pc, idx, j, re, im, part == 0, C::KIND != KIND_RECUR || part == 1);
+    flush_node<C>(P, g, tv, pc, iSnap, lane, k, ma, pa);
   }
 }
 
@@ -1338,7 +1383,7 @@ SRB_HD void warp_task(const Params& P, uint32_t vd, uint32_t pc, WarpSmem<C>& sm
       }
       SRB_LANES_BEGIN
         if constexpr (C::KIND == KIND_LITERAL) lit_flush_lane<C>(P, g, tv, pc, iSnap, lane, SRB_ST);
-        else flush_lane<C>(P, g, tv, pc, iSnap, lane, st);
+        else flush_lane<C>(P, g, tv, pc, iSnap, lane, st, C::PAIR ? nullptr : reinterpret_cast<typename C::TM*>(&sm));
       SRB_LANES_END
       if constexpr (C::MMA) {
         SRB_LANES_BEGIN
