@@ -737,7 +737,13 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   uint64_t maxPC = t->nTracks ? t->nTracks : 1;
   const uint64_t slabCap = unlimited ? (uint64_t)(1ull << 30) / (p->slabDoubles * 8) : scratch_bytes / (p->slabDoubles * 8);
   maxPC = std::min<uint64_t>(maxPC, 1 + slabCap);
-  maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, (64 * slots) / p->nVDtiles));
+  // ... and by the L2: every direction block of a particle chunk streams the chunk's tracks, concurrently running blocks
+  // drift apart, so a chunk that does not stay L2-resident is re-read from DRAM by most of them (12 500 x 10^4 steps in
+  // 37 chunks of 243 MB: 262 GB of DRAM traffic per launch against 6 GB of tracks, profiles/r02_ncu_headline.json of
+  // that build).  Chunks of <= 32 MB of streamed input (a quarter of the 126 MB L2) when tracks and scratch allow.
+  const uint64_t streamBytes = (p->preDoubles ? p->preDoubles * 8 : 0) + (p->ws ? 0 : 24 * t->totalSteps_host);
+  const uint64_t l2PC = (streamBytes + (32ull << 20) - 1) / (32ull << 20);
+  maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(std::max<uint64_t>(1, (64 * slots) / p->nVDtiles), l2PC));
   maxPC = std::min<uint64_t>(maxPC, 4096);
   maxPC = std::min<uint64_t>(maxPC, std::max<uint64_t>(1, 0x7fffffffull / p->nVDtiles));   // gridDim.x limit
   double best = -1.0; uint32_t bestN = 1;
