@@ -743,7 +743,6 @@ SRB_HD void rec_row(const WarpSmem<C>& sm, int s, typename C::TM* R) {
       if (4 * i + 2 < N) R[4 * i + 2] = t.z;
       if (4 * i + 3 < N) R[4 * i + 3] = t.w;
     }
-    return;
   } else if constexpr (sizeof(TM) == 8 && C::NREC % 2 == 0) {
     const double2* q = reinterpret_cast<const double2*>(&sm.rec[s][0]);
 #pragma unroll
@@ -752,11 +751,12 @@ SRB_HD void rec_row(const WarpSmem<C>& sm, int s, typename C::TM* R) {
       if (2 * i + 0 < N) R[2 * i + 0] = t.x;
       if (2 * i + 1 < N) R[2 * i + 1] = t.y;
     }
-    return;
-  }
+  } else
 #endif
+  {
 #pragma unroll
-  for (int k = 0; k < N; k++) R[k] = sm.rec[s][k];
+    for (int k = 0; k < N; k++) R[k] = sm.rec[s][k];
+  }
 }
 
 // one full step of one tile: v0, v1 = first two nodes of the tile, then the three-term recurrence
