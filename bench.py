@@ -612,7 +612,7 @@ def main():
     p.add_argument('--e2e-steps', type=int, default=2)
     p.add_argument('--cpu-particles', type=int, default=8, help='CPU baseline sample (reference kernels, fast build)')
     p.add_argument('--parity-particles', type=int, default=2, help='of those, checked on the GPU against the strict build')
-    p.add_argument('--ref-particles', type=int, default=2)
+    p.add_argument('--ref-particles', type=int, default=4, help='--impl reference: particles per step (about 4 s each on 16 cores)')
     p.add_argument('--fp32-steps', type=int, default=1, help='timed launches per float mode on top of one (besides the warm-up)')
     p.add_argument('--fp32-literal-fraction', type=float, default=0.2,
                    help='share of the shard the literal-fp32 leg integrates (same recipe, linear in particles)')
