@@ -69,8 +69,9 @@ extern "C" {
                                field); fp64: the accumulation over steps runs as a GEMM on the FP64 tensor cores
                                (DMMA.8x8x4) when tile width x components is a multiple of 8 */
 #define SRB_PHASOR_PAIR_FMA 4 /* the pair kernel with the accumulation kept on the scalar FP64 pipe (DFMA) */
-#define SRB_PHASOR_DREC 5   /* direct layout, per-lane recurrence along omega + per-update correction onto the reference's
-                               rounded phase: phases of any magnitude (near field at large L), uniform grids, fp64 */
+#define SRB_PHASOR_DREC 5   /* direct layout, per-lane recurrence along omega + per-update first-order correction onto the
+                               reference's rounded phase: phases up to 3e10 rad (near field at large L; refused beyond:
+                               one ulp of the phase then exceeds 1e-5 rad), uniform grids, fp64 */
 
 /* srb_launch_info.kind when the kernel was chosen on the device (read counters[2]) */
 #define SRB_KIND_ON_DEVICE (-1)

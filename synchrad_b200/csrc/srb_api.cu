@@ -388,6 +388,10 @@ __global__ void k_prepass(const srb::Params P, double* __restrict__ pre, uint64_
 // pass the Nyquist guard at every node of the grid ("full"), at some nodes only ("partial"), or nowhere.
 // The pair kernel is faster on full steps (5.0 vs 6.0 FP64 ops per update) but ~3x slower on partial
 // ones (its accumulators are sums over node PAIRS), so the planner picks by this ratio.
+// The corrected-recurrence kernel rotates by (1 + i c), c ~ one ulp of the phase: its second-order term c^2 / 2 stays
+// below 1e-10 up to phases of ~6e10 rad (ulp 1.4e-5); beyond this limit the planner takes the direct kernel instead
+// (found by the round-2 fuzz run: near field, omega * L = 7.5e11 rad, 1.2e-9 off).
+#define SRB_DREC_MAX_PHASE 3.0e10
 __global__ void k_probe(const srb::Params P, uint64_t total, double wFirst, double wLast, unsigned int* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t h = (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
@@ -410,6 +414,7 @@ __global__ void k_probe(const srb::Params P, uint64_t total, double wFirst, doub
   // passing steps whose phase at the last node is beyond the 2^18 limit of the phase-tracking kernels (SI-unit tracks)
   const double tau = (double)(P.itStart[a] + (uint32_t)it) * P.dt - (x[gs] * sT * cP + y[gs] * sT * sP + z[gs] * cT);
   if (some && fabs(wLast * tau) > 262144.0) atomicAdd(out + 3, 1u);
+  if (some && fabs(wLast * tau) > SRB_DREC_MAX_PHASE) atomicAdd(out + 4, 1u);     // beyond the corrected recurrence's first-order correction
 }
 
 // phasor = AUTO: the decision from the probe counts, on the device (no host round trip): partial steps cost the pair
@@ -419,7 +424,7 @@ __global__ void k_decide(const unsigned int* probe, int32_t* sel, unsigned long 
   const bool preferRecur = probe[0] > 0 && (double)probe[2] > 0.1 * (double)probe[1];
   // mostly all-pass steps with huge phases (SI-unit tracks): neither phase-tracking kernel applies (every step would be
   // evaluated node by node), the corrected-recurrence kernel does (srb_drec.cuh)
-  const bool big = haveDrec && 2.0 * (double)probe[3] > (double)probe[1] + (double)probe[2];
+  const bool big = haveDrec && probe[4] == 0u && 2.0 * (double)probe[3] > (double)probe[1] + (double)probe[2];
   sel[0] = preferRecur ? srb::KIND_RECUR : (big ? srb::KIND_DREC : srb::KIND_PAIR);
   if (counters) counters[2] = (unsigned long long)sel[0];
 }
@@ -658,9 +663,11 @@ int make_plan(const srb_grid* g, const srb_tracks* t, size_t scratch_bytes, bool
   // kernel (srb_drec.cuh: direct layout, per-update correction onto the rounded phase) takes over.
   if (g->phasor == SRB_PHASOR_AUTO && g->mode == SRB_MODE_NEAR && g->dtype == SRB_DTYPE_F64 && uniform &&
       std::fabs(g->omega_last_host * g->L_screen) > 262144.0)
-    p->kind = KIND_DREC;
+    p->kind = std::fabs(g->omega_last_host * g->L_screen) <= SRB_DREC_MAX_PHASE ? KIND_DREC : KIND_DIRECT;
   if (g->phasor == SRB_PHASOR_DREC) {
     if (!uniform || g->dtype != SRB_DTYPE_F64) return fail("the corrected-recurrence kernel needs fp64 and an ascending uniform omega grid");
+    if (g->mode == SRB_MODE_NEAR && std::fabs(g->omega_last_host * g->L_screen) > SRB_DREC_MAX_PHASE)
+      return fail("the corrected-recurrence kernel is first-order in one ulp of the phase: omega * L beyond 3e10 rad needs phasor = direct (or auto)");
     p->kind = KIND_DREC;
   }
   if (forceDrec && uniform && g->dtype == SRB_DTYPE_F64) p->kind = KIND_DREC;     // third candidate of phasor = AUTO (far field)

@@ -202,6 +202,28 @@ def test_auto_takes_corrected_recurrence_for_all_pass_steps_with_huge_phases(cud
     assert run_gpu(a32, tracks, dt).last_run['kernel'] == 'pair'
 
 
+def test_near_field_beyond_the_corrected_recurrence_range(cuda_lib, oracle):
+    """omega * L = 7.5e11 rad (found by tools/extended_validation2.py): one ulp of the phase is 1.7e-4 rad, the
+    first-order correction of the corrected-recurrence kernel is no longer enough (1.2e-9 off) -- 'auto' takes the
+    direct kernel beyond 3e10 rad, an explicit 'drec' is refused."""
+    tracks, dt = cases.c5_tracks_numpy(2, 100, seed=5)
+    args = cases.c5_args(grid=(256, 3, 3))
+    args['mode'] = 'near'
+    args['grid'][0] = (args['grid'][0][0], 1.2e7)
+    args['grid'][1] = (0.0, 300.0)
+    ref = oracle.calculate_spectrum(args, tracks, dt, L_screen=1e4, nSnaps=2)
+    calc = run_gpu(args, tracks, dt, L_screen=1e4, nSnaps=2)
+    assert calc.last_run['kernel'] == 'direct', calc.last_run
+    assert_close(calc, ref['radiation'])
+    with pytest.raises(RuntimeError, match='first-order'):
+        run_gpu(args, tracks, dt, phasor='drec', L_screen=1e4, nSnaps=2)
+    args['grid'][0] = (args['grid'][0][0], 3.0e5)                     # omega * L = 1.9e10: inside the range
+    ref = oracle.calculate_spectrum(args, tracks, dt, L_screen=1e4, nSnaps=2)
+    calc = run_gpu(args, tracks, dt, L_screen=1e4, nSnaps=2)
+    assert calc.last_run['kernel'] == 'drec', calc.last_run
+    assert_close(calc, ref['radiation'])
+
+
 def test_c3_like_si_units(cuda_lib, oracle):
     tracks, dt, info = cases.wiggler_tracks(8, 256, si_scale=1e-3)
     args = cases.wiggler_args(info, grid=(256, 8, 4), si_scale=1e-3)
@@ -535,7 +557,11 @@ def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
             else:
                 phasors = ('auto', 'recur', 'direct', 'drec') if far_plain else ('auto', 'direct', 'drec')
             for phasor in phasors:
-                calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
+                try:
+                    calc = run_gpu(A, tracks, dt, phasor=phasor, **kw)
+                except RuntimeError as err:      # near field, omega * L beyond 3e10 rad: an explicit 'drec' is refused
+                    assert phasor == 'drec' and 'first-order' in str(err), (seed, i, phasor, err)
+                    continue
                 e = fuzzcases.vector_errors(calc.Data['radiation'], ref['radiation'])
                 assert e < 1e-9, (seed, i, phasor, e, A['grid'], A.get('mode'), A.get('Features'), kw)
 
