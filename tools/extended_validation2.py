@@ -52,6 +52,23 @@ for seed in range(500, 500 + (int(sys.argv[1]) if len(sys.argv) > 1 else 20)):
             if not (e <= tol):
                 fails += 1
                 print('FAIL', seed, i, key, e, A['grid'], A.get('mode'), A.get('Features'), kw, c.last_run['kernel'])
+        # single precision: the mixed mode against the fp64 oracle, the literal mode against the oracle's fp32 restatement
+        # of the reference (both 1e-4, north_star's single-precision tolerance)
+        os.environ.pop('SRB_TIME_SPLIT', None)
+        if seed % 2 == 0:
+            A32 = dict(A); A32['dtype'] = 'float'
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref32 = rp.calculate_spectrum(A32, tracks, dt, **kw)
+            for mode, want in (('mixed', ref), ('literal', ref32)):
+                Am = dict(A32); Am['float_mode'] = mode
+                c = gpu(Am, tracks, dt, **kw)
+                e = fuzzcases.vector_errors(c.Data['radiation'], want['radiation'])
+                key = ('auto', mode, 'f32')
+                worst[key] = max(worst.get(key, 0.0), e); n += 1
+                kinds[c.last_run['kernel']] = kinds.get(c.last_run['kernel'], 0) + 1
+                if not (e <= 1e-4):
+                    fails += 1
+                    print('FAIL', seed, i, key, e, A['grid'], A.get('mode'), A.get('Features'), kw, c.last_run['kernel'])
 os.environ.pop('SRB_TIME_SPLIT', None)
 print(f'fuzz: {n} runs, {fails} failures, {time.time() - t0:.0f} s; kernels that ran: {kinds}')
 for k in sorted(worst, key=str):
