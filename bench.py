@@ -448,6 +448,7 @@ def run_product(a):
                             'of_which_file_read': lr['file_read_s'], 'gpu_integrate': lr['integrate_ms'] * 1e-3,
                             'call_total': runs[-1][0]},
                 'h2d_bytes_per_call': lr['h2d_bytes'], 'd2h_bytes_per_call': lr['d2h_bytes'],
+                'pipelined_batches': lr['batches'],     # file reading + packing of batch k+1 overlaps the kernel on batch k
                 'spectrum_file_bytes': os.path.getsize(fs), 'tracks_file_write_s_untimed': write_s,
             }
         del tr_list

@@ -244,8 +244,10 @@ class SynchRad(Utilities):
             budget = self.Args.get('max_batch_bytes')
             if budget is None:
                 free, _ = torch.cuda.mem_get_info(self.device)
-                budget = int(0.6 * free)
-            spans = host.split_batches(lengths, max(int(budget) // 96, 1))
+                # large sets also go in batches of ~256 MB so that host packing / file reading overlaps the kernel
+                spans = host.pipelined_batches(lengths, max(int(0.6 * free) // 96, 1))
+            else:
+                spans = host.split_batches(lengths, max(int(budget) // 96, 1))
             batches = spans
         res, h2d, upd, ms = None, 0, 0, 0.0
         # Track sets larger than the device: batch k+1 is packed on the host and uploaded on a second stream while batch

@@ -115,6 +115,20 @@ def test_split_batches():
     assert host.split_batches([500], 100) == [(0, 1)]
 
 
+def test_pipelined_batches():
+    # small sets: one batch; the device bound still applies
+    assert host.pipelined_batches([10, 10, 10], 10 ** 9) == [(0, 3)]
+    assert host.pipelined_batches([60, 60, 60], 100) == [(0, 1), (1, 2), (2, 3)]
+    # up to 1.5 x the batch size stays whole
+    assert host.pipelined_batches([100] * 14, 10 ** 9, batch_bytes=48 * 1000) == [(0, 14)]
+    # above: equal batches of about the batch size, every track exactly once, in order
+    spans = host.pipelined_batches([100] * 64, 10 ** 9, batch_bytes=48 * 1000)
+    assert spans[0][0] == 0 and spans[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert len(spans) == 8 and max(b - a for a, b in spans) == 9       # ceil(6400 / 7) = 915 samples -> 9 whole tracks
+    # the device bound wins when it is the smaller one
+    assert len(host.pipelined_batches([100] * 64, 300, batch_bytes=48 * 1000)) == 22
+
+
 def test_balanced_partition_covers_every_track_once():
     """Extension Args['partition']='balanced' (SURVEY §8e): contiguous slices of near-equal work sum(n_p - 1); the
     default stays the reference's tracks[rank::size]."""
