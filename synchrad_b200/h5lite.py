@@ -288,6 +288,8 @@ class _RNode:
     def __getitem__(self, path):
         if path == ():
             return self._rd.read_dataset(self._addr)
+        if not isinstance(path, str):       # h5py's `dset[::2, 3, :]`: whole dataset read, then NumPy indexing
+            return self._rd.read_dataset(self._addr)[path]
         node = self
         for part in [p for p in path.split('/') if p]:
             kids = node._children()

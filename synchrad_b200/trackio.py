@@ -34,7 +34,9 @@ def read_header(path):
     f = _h5.File(path, 'r')
     try:
         cdt = float(f['misc/cdt'][()])
-        rng = tuple(int(v) for v in f['misc/it_range'][()]) if 'it_range' in f['misc'].keys() else None
+        rng = np.asarray(f['misc/it_range'][()], dtype=np.double) if 'it_range' in f['misc'].keys() else None
+        # a converter that wrote no track leaves [inf, 0] (converters.py:86-87,124): no usable range
+        rng = tuple(int(v) for v in rng) if rng is not None and np.all(np.isfinite(rng)) else None
         n = int(f['misc/N_particles'][()])
     finally:
         f.close()
