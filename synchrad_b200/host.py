@@ -305,14 +305,14 @@ def split_batches(lengths, max_steps):
 PIPELINE_BATCH_BYTES = 256 << 20      # host bytes of coordinates (48 per sample) per pipelined batch
 
 
-def pipelined_batches(lengths, device_steps, batch_bytes=PIPELINE_BATCH_BYTES):
+def pipelined_batches(lengths, device_steps, batch_bytes=None):
     """split_batches for a track list that is still to be packed: sets above 1.5 x `batch_bytes` of coordinates are cut
     into equal batches of about `batch_bytes`, so that packing (or reading from the tracks file) batch k+1 into pinned
     memory overlaps the integration of batch k and the pinned buffers are recycled instead of growing with the set
     (the reference's loop, calc.py:257-267, converts, uploads and launches one track at a time, serially).
     `device_steps` bounds a batch by what fits on the device."""
     total = int(sum(int(n) for n in lengths))
-    per_batch = max(int(batch_bytes) // 48, 1)
+    per_batch = max(int(PIPELINE_BATCH_BYTES if batch_bytes is None else batch_bytes) // 48, 1)
     steps = int(device_steps)
     if total * 2 > per_batch * 3:
         n_b = -(-total // per_batch)

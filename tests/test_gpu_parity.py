@@ -540,6 +540,59 @@ def test_file_tracks_to_file_spectrum(cuda_lib, oracle, tmp_path):
     assert_close(calc, ref2['radiation'])
 
 
+def test_converted_tracks_file_through_the_path(cuda_lib, oracle, tmp_path):
+    """The PIC flow of tutorials/PIC: time series with particles entering / leaving -> tracksFromOPMD -> tracks file
+    -> calculate_spectrum(file_tracks=...); it_range comes from the file, every piece carries its it_start."""
+    from golden import converter_cases as cc
+    from synchrad.calc import SynchRad
+    from synchrad.utils import tracksFromOPMD
+    from synchrad_b200 import trackio
+    tracks, dt, info = cases.undulator_tracks(6, seed=4)
+    n_it = len(tracks[0][0])
+    series = {v: np.array([t[k] for t in tracks]).T.copy() for k, v in enumerate(('x', 'y', 'z', 'ux', 'uy', 'uz'))}
+    series['w'] = np.tile([t[6] for t in tracks], (n_it, 1)).astype(np.double)
+    for v in series:
+        series[v][:300, 1] = np.nan          # enters late
+        series[v][900:, 2] = np.nan          # leaves early
+        series[v][500:520, 3] = np.nan       # absent for a while: two tracks
+        series[v][n_it - 5:, 4] = np.nan
+    data = [{v: series[v][k] for v in series} for k in range(n_it)]
+    ts = cc.FakeTimeSeries(data, np.arange(n_it), np.arange(n_it) * (dt / cc.C))
+    ts.n_all = 6
+    ftr = str(tmp_path / 'tracks.h5')
+    tracksFromOPMD(ts, cc.FakeTracker(ts, species='e'), 0, fname=ftr)
+    cdt, rng, n = trackio.read_header(ftr)
+    assert n == 7 and rng == (0, n_it)
+    lists = trackio.read_tracks(ftr, range(n))
+    assert sorted(t[7] for t in lists) == [0, 0, 0, 0, 0, 300, 520]
+    args = cases.undulator_args(info, grid=(64, 6, 4))
+    calc = SynchRad(dict(args))
+    calc.calculate_spectrum(file_tracks=ftr, comp='total', nSnaps=3, verbose=False)
+    ref = oracle.calculate_spectrum(args, lists, cdt, comp='total', nSnaps=3, it_range=rng)
+    assert_close(calc, ref['radiation'])
+    assert calc.total_weight == pytest.approx(ref['total_weight'], rel=1e-15)
+
+
+def test_pipelined_batches_on_gpu(cuda_lib, oracle, monkeypatch):
+    """Large track sets are packed and integrated in ~256 MB batches (host.pipelined_batches) so that host packing
+    overlaps the kernel; here the batch size is shrunk so that a small set takes that route."""
+    from synchrad.calc import SynchRad
+    from synchrad_b200 import host
+    tracks, dt, info = cases.undulator_tracks(9, seed=6)
+    args = cases.undulator_args(info, grid=(64, 6, 4))
+    one = SynchRad(dict(args))
+    one.calculate_spectrum([list(t) for t in tracks], timeStep=dt, comp='cartesian_complex', nSnaps=2, verbose=False)
+    monkeypatch.setattr(host, 'PIPELINE_BATCH_BYTES', 48 * int(2.5 * len(tracks[0][0])))      # -> 4 equal shares of 9 tracks = two whole tracks per batch
+    many = SynchRad(dict(args))
+    many.calculate_spectrum([list(t) for t in tracks], timeStep=dt, comp='cartesian_complex', nSnaps=2, verbose=False)
+    assert one.last_run['batches'] == 1 and many.last_run['batches'] == 5
+    ref = oracle.calculate_spectrum(args, tracks, dt, comp='cartesian_complex', nSnaps=2)
+    assert_close(many, ref['radiation'])
+    for k, v in one.Data['radiation'].items():
+        assert np.abs(many.Data['radiation'][k] - v).max() <= 1e-12 * np.abs(v).max()
+    assert many.last_run['passed_updates'] == one.last_run['passed_updates']
+
+
 # ---------------------------------------------------------------------------- differential fuzz
 @pytest.mark.parametrize('seed', [10, 11, 12])
 def test_random_problems_match_oracle_on_gpu(cuda_lib, oracle, seed):
