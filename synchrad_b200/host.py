@@ -256,33 +256,53 @@ def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
         P.snapStride = 0
         P.itSnaps = alloc((nSnaps,), np.uint32)
         P.itSnaps[:] = snap_iterations(it_range, nSnaps)
-    upd = 0
-    for i, t in enumerate(tracks):
-        o, e = int(P.offsets[i]), int(P.offsets[i + 1])
-        direct = getattr(t, 'read_into', None)      # lazy file track: file -> packed buffer, no intermediate array
+    in_memory = n > 0 and all(getattr(t, 'read_into', None) is None for t in tracks)
+    if in_memory:
+        # track lists held in memory: one concatenation per coordinate (astype(dtype) happens inside) instead of
+        # 6 slice assignments per track -- the reference converts and uploads array by array (calc.py:579-603)
         for c in range(6):
-            if direct is not None:
-                try:
-                    direct(c, P.coords[c][o:e])
-                except ValueError as exc:
-                    raise ValueError(f'track {i}: coordinate arrays differ in length ({exc})') from None
-                continue
-            a = np.asarray(t[c])
-            if a.size != e - o:
-                raise ValueError(f'track {i}: coordinate arrays differ in length')
-            P.coords[c][o:e] = a            # astype(dtype) happens in the assignment
-        P.w[i] = weights[i]
-        m = e - o
-        if it_range is None:
-            P.itStart[i] = 0
-            P.itEnd[i] = m
-            P.itSnaps[i, :] = snap_iterations((0, m), nSnaps)
-            end = m
-        else:
-            P.itStart[i] = t[7] if len(t) == 8 else 0
-            P.itEnd[i] = it_range[-1]
-            end = int(it_range[-1])
-        upd += max(0, min(m - 1, end - 1))
+            cols = [t[c] for t in tracks]
+            cols = [a if type(a) is np.ndarray and a.ndim == 1 else np.asarray(a).reshape(-1) for a in cols]
+            sizes = np.fromiter((a.size for a in cols), dtype=np.uint64, count=n)
+            if not np.array_equal(sizes, lens):
+                raise ValueError(f'track {int(np.flatnonzero(sizes != lens)[0])}: coordinate arrays differ in length')
+            if P.total:
+                np.concatenate(cols, out=P.coords[c][:P.total], casting='unsafe')
+    else:
+        for i, t in enumerate(tracks):
+            o, e = int(P.offsets[i]), int(P.offsets[i + 1])
+            direct = getattr(t, 'read_into', None)  # lazy file track: file -> packed buffer, no intermediate array
+            for c in range(6):
+                if direct is not None:
+                    try:
+                        direct(c, P.coords[c][o:e])
+                    except ValueError as exc:
+                        raise ValueError(f'track {i}: coordinate arrays differ in length ({exc})') from None
+                    continue
+                a = np.asarray(t[c])
+                if a.size != e - o:
+                    raise ValueError(f'track {i}: coordinate arrays differ in length')
+                P.coords[c][o:e] = a        # astype(dtype) happens in the assignment
+    if n:
+        P.w[:n] = np.asarray(weights, dtype=np.double)[:n]
+    m = lens.astype(np.int64)
+    if it_range is None:
+        if n:
+            P.itStart[:n] = 0
+            P.itEnd[:n] = m
+            for length in np.unique(m):     # one snapshot row per distinct track length (calc.py:297-301, 626-630)
+                P.itSnaps[:n][m == length] = snap_iterations((0, int(length)), nSnaps)
+        end = m
+    else:
+        if n:
+            starts = np.fromiter((t[7] if len(t) == 8 else 0 for t in tracks), dtype=np.int64, count=n)
+            if starts.min() < 0 or starts.max() > 0xFFFFFFFF:
+                raise OverflowError(f'track {int(np.flatnonzero((starts < 0) | (starts > 0xFFFFFFFF))[0])}: '
+                                    'it_start does not fit uint32 (calc.py:599)')
+            P.itStart[:n] = starts
+            P.itEnd[:n] = it_range[-1]
+        end = np.full(n, int(it_range[-1]), dtype=np.int64)
+    upd = int(np.maximum(0, np.minimum(m - 1, end - 1)).sum()) if n else 0
     P.updates_per_node = upd
     return P
 
