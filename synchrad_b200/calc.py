@@ -243,7 +243,10 @@ class SynchRad(Utilities):
             lengths = [host.track_length(t) for t in particleTracks]
             budget = self.Args.get('max_batch_bytes')
             if budget is None:
-                free, _ = torch.cuda.mem_get_info(self.device)
+                # the device bound only matters for sets of GBs; cudaMemGetInfo costs ~1.3 ms, 6 x the kernel time of a
+                # single-electron call, so it is asked only then
+                need = 96 * int(sum(lengths))
+                free = torch.cuda.mem_get_info(self.device)[0] if need > (1 << 30) else (4 << 30)
                 # large sets also go in batches of ~256 MB so that host packing / file reading overlaps the kernel
                 spans = host.pipelined_batches(lengths, max(int(0.6 * free) // 96, 1))
             else:
@@ -260,7 +263,7 @@ class SynchRad(Utilities):
                     t0 = time.perf_counter()
                     alloc = engine.PinnedAlloc()
                     packed = host.pack_tracks(particleTracks[b[0]:b[1]], weights[b[0]:b[1]], np.double, it_range,
-                                              nSnaps, alloc)
+                                              nSnaps, alloc, lengths=lengths[b[0]:b[1]])
                     t_pack += time.perf_counter() - t0
                 res = engine.integrate(self.Args, self.dtype, self._grid, packed, comp, nSnaps,
                                        spectra=None if res is None else res.spectra,

@@ -225,7 +225,7 @@ def track_length(t):
     return int(n) if n is not None else int(np.asarray(t[0]).size)
 
 
-def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
+def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None, lengths=None):
     """Concatenate tracks into SoA arrays of `dtype` (the product always packs float64: see
     grid_tables for why the reference's astype(float32) is not reproduced in 'float' mode).
 
@@ -233,11 +233,12 @@ def pack_tracks(tracks, weights, dtype, it_range, nSnaps, alloc=None):
     weights: per-track weights after normalisation
     it_range None -> per track it_start=0, it_range=(0, n), own snapshot row (calc.py:297-301)
     alloc(shape, dtype) -> writable ndarray (e.g. a view of a pinned torch tensor)
+    lengths: the tracks' sample counts when the caller already has them
     """
     if alloc is None:
         alloc = lambda shape, dt: np.empty(shape, dtype=dt)
     n = len(tracks)
-    lens = np.fromiter((track_length(t) for t in tracks), dtype=np.uint64, count=n)
+    lens = np.fromiter((track_length(t) for t in tracks) if lengths is None else lengths, dtype=np.uint64, count=n)
     P = PackedTracks()
     P.n = n
     P.offsets = alloc((n + 1,), np.uint64)
@@ -322,20 +323,31 @@ def split_batches(lengths, max_steps):
     return out
 
 
-PIPELINE_BATCH_BYTES = 256 << 20      # host bytes of coordinates (48 per sample) per pipelined batch
+PIPELINE_BATCH_BYTES = 256 << 20      # host bytes of coordinates (48 per sample) per pipelined batch: upper bound
+PIPELINE_MIN_BATCH_BYTES = 16 << 20   # and lower bound (smaller batches cost more kernel efficiency than packing hides)
 
 
 def pipelined_batches(lengths, device_steps, batch_bytes=None):
-    """split_batches for a track list that is still to be packed: sets above 1.5 x `batch_bytes` of coordinates are cut
-    into equal batches of about `batch_bytes`, so that packing (or reading from the tracks file) batch k+1 into pinned
-    memory overlaps the integration of batch k and the pinned buffers are recycled instead of growing with the set
-    (the reference's loop, calc.py:257-267, converts, uploads and launches one track at a time, serially).
-    `device_steps` bounds a batch by what fits on the device."""
+    """split_batches for a track list that is still to be packed: sets above 24 MB of coordinates are cut into equal
+    batches -- a quarter of the set each, at least 16 MB, at most `batch_bytes` (256 MB) -- so that packing (or reading
+    from the tracks file) batch k+1 into pinned memory overlaps the integration of batch k and the pinned buffers are
+    recycled instead of growing with the set (the reference's loop, calc.py:257-267, converts, uploads and launches one
+    track at a time, serially).  Measured (tools/c3_batches.py, profiles/r02_host_overhead.txt): C4 (92 MB) 1499 ->
+    1457 ms in 4 batches, the 600 MB file leg of bench.py 1.39 -> 1.24 s in 4; C3 (12 MB) is slower in 2 (35.9 -> 36.5 ms)
+    and stays whole.  `device_steps` bounds a batch by what fits on the device."""
     total = int(sum(int(n) for n in lengths))
-    per_batch = max(int(PIPELINE_BATCH_BYTES if batch_bytes is None else batch_bytes) // 48, 1)
+    hi = int(PIPELINE_BATCH_BYTES if batch_bytes is None else batch_bytes)
+    lo = min(PIPELINE_MIN_BATCH_BYTES, hi)
+    per_batch = max(min(hi, max(48 * total // 4, lo)) // 48, 1)
     steps = int(device_steps)
     if total * 2 > per_batch * 3:
         n_b = -(-total // per_batch)
+        if -(-total // n_b) * 5 < steps * 4:          # well inside the device bound: balanced shares of whole tracks
+            cum = np.cumsum(np.asarray(lengths, dtype=np.int64))
+            cuts = np.searchsorted(cum, total * np.arange(1, n_b) / n_b, side='left') + 1
+            cuts = np.unique(np.clip(cuts, 1, len(lengths) - 1)) if len(lengths) > 1 else np.zeros(0, dtype=np.int64)
+            edges = [0] + [int(c) for c in cuts] + [len(lengths)]
+            return [(a, b) for a, b in zip(edges, edges[1:]) if b > a]
         steps = min(steps, -(-total // n_b))
     return split_batches(lengths, max(steps, 1))
 

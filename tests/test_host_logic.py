@@ -116,15 +116,31 @@ def test_split_batches():
 
 
 def test_pipelined_batches():
-    # small sets: one batch; the device bound still applies
+    def ok(spans, n):
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] and a[1] > a[0] for a, b in zip(spans, spans[1:]))
+        return spans
+    # small sets (below 24 MB of coordinates): one batch; the device bound still applies
     assert host.pipelined_batches([10, 10, 10], 10 ** 9) == [(0, 3)]
     assert host.pipelined_batches([60, 60, 60], 100) == [(0, 1), (1, 2), (2, 3)]
-    # up to 1.5 x the batch size stays whole
+    assert host.pipelined_batches([256] * 1000, 10 ** 9) == [(0, 1000)]                       # C3: 12 MB
+    # above: a quarter of the set per batch, balanced over whole tracks ...
+    assert ok(host.pipelined_batches([192] * 10000, 10 ** 9), 10000) == [(0, 2500), (2500, 5000), (5000, 7500), (7500, 10000)]
+    spans = ok(host.pipelined_batches([10000] * 1250, 10 ** 9), 1250)                         # bench.py's file leg: 600 MB
+    assert len(spans) == 4 and {b - a for a, b in spans} <= {312, 313}
+    # ... at most 256 MB each
+    spans = ok(host.pipelined_batches([10000] * 12500, 10 ** 9), 12500)
+    assert len(spans) == 23 and max(b - a for a, b in spans) <= 544
+    # explicit batch size (tests): up to 1.5 x stays whole, above it equal shares
     assert host.pipelined_batches([100] * 14, 10 ** 9, batch_bytes=48 * 1000) == [(0, 14)]
-    # above: equal batches of about the batch size, every track exactly once, in order
-    spans = host.pipelined_batches([100] * 64, 10 ** 9, batch_bytes=48 * 1000)
-    assert spans[0][0] == 0 and spans[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
-    assert len(spans) == 8 and max(b - a for a, b in spans) == 9       # ceil(6400 / 7) = 915 samples -> 9 whole tracks
+    spans = ok(host.pipelined_batches([100] * 64, 10 ** 9, batch_bytes=48 * 1000), 64)
+    assert len(spans) == 7 and {b - a for a, b in spans} <= {9, 10}
+    # ragged lengths: every track exactly once, shares within one track of each other
+    L = list(np.random.default_rng(0).integers(10, 100000, 3000))
+    spans = ok(host.pipelined_batches(L, 10 ** 12), len(L))
+    sizes = [sum(L[a:b]) for a, b in spans]
+    assert max(sizes) - min(sizes) <= 2 * max(L)
+    # a single long track cannot be cut
+    assert host.pipelined_batches([10 ** 7], 10 ** 12) == [(0, 1)]
     # the device bound wins when it is the smaller one
     assert len(host.pipelined_batches([100] * 64, 300, batch_bytes=48 * 1000)) == 22
 
