@@ -13,6 +13,7 @@ Not supported (raises): chunked/compressed datasets, new-style groups (v2 object
 The writer emits superblock v0, one symbol-table group per group, contiguous datasets, fixed-length
 UTF-8 strings.
 """
+import mmap
 import struct
 
 import numpy as np
@@ -28,14 +29,29 @@ class _Reader:
         self.f = open(path, 'rb')
         self.base = 0
         self._heaps, self._gheaps, self._kids = {}, {}, {}
-        self._superblock()
+        try:        # metadata (tens of small reads per object) through a mapping: no seek/read system calls
+            self.mm = mmap.mmap(self.f.fileno(), 0, access=mmap.ACCESS_READ)
+        except (ValueError, OSError):
+            self.mm = None
+        try:
+            self._superblock()
+        except Exception:
+            self.close()
+            raise
 
     def close(self):
+        if self.mm is not None:
+            self.mm.close()
+            self.mm = None
         self.f.close()
 
     def rd(self, addr, n):
-        self.f.seek(self.base + addr)
-        b = self.f.read(n)
+        a = self.base + addr
+        if self.mm is not None:
+            b = self.mm[a:a + n]
+        else:
+            self.f.seek(a)
+            b = self.f.read(n)
         if len(b) != n:
             raise IOError('h5lite: truncated file')
         return b

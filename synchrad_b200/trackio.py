@@ -67,7 +67,8 @@ class FileTrack:
 
     def __init__(self, group):
         self._g = group
-        self.n = int(group['x'].shape[0]) if len(group['x'].shape) else 1
+        shape = group['x'].shape
+        self.n = int(shape[0]) if len(shape) else 1
         self._w = float(group['w'][()])
         self.it_start = int(group['it_start'][()]) if 'it_start' in group.keys() else 0
 
