@@ -288,7 +288,10 @@ class SynchRad(Utilities):
         cnt = res.counters
         if self.size > 1:                       # replaces _gather_result_mpi (calc.py:560-571)
             from .dist import reduce_to_root
+            # the update count travels with the guard counters, so that root reports all three for the whole job
+            cnt = torch.cat([cnt, torch.tensor([upd], dtype=cnt.dtype, device=cnt.device)])
             dev_out, self.total_weight, cnt = reduce_to_root(self.comm, dev_out, self.total_weight, cnt)
+            upd = int(cnt[2].item())
         self.Data['radiation'] = {k: d.cpu().numpy() for k, d in zip(keys, dev_out)}
         # calc.py:475-480 keeps the form-factor table in Data as well (there a device array; here the host table)
         self.Data['FormFactor'] = host.form_factor(self.Args)

@@ -30,19 +30,31 @@ def build(so=None, defines=()):
 def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSnaps=1,
         sigma_particle=0, kind='recur', tw=None, nPC=1, prepass=True, nTS=1, variant=None):
     """Returns (radiation dict in host layout, counters).  variant = (name, defines): a separately built emulator."""
-    so = _SO if variant is None else os.path.join(_HERE, f'libsrb_emu_{variant[0]}.so')
-    build(so, () if variant is None else variant[1])
-    lib = ctypes.CDLL(so)
     A = dict(Args)
     A, dtype = host.init_args(A)
     A['sigma_particle'] = dtype(sigma_particle)
     if A['mode'] == 'near':
         A['L_screen'] = L_screen
     A['timeStep'] = dtype(timeStep)
-    T = host.grid_tables(A)
     literal_pre = A.get('float_mode') == 'literal' and A.get('dtype', 'double') != 'double'
     weights = [float(np.float32(t[6])) if literal_pre else t[6] for t in tracks]
     pk = host.pack_tracks(tracks, weights, np.double, it_range, nSnaps)
+    spectra, cnt = run_packed(A, dtype, pk, timeStep, comp, nSnaps, kind=kind, tw=tw, nPC=nPC, prepass=prepass, nTS=nTS,
+                              variant=variant)
+    rad = {k: np.ascontiguousarray(s.swapaxes(-1, -3)) for k, s in zip(host.COMP_KEYS[comp], spectra)}
+    return rad, cnt
+
+
+def run_packed(A, dtype, pk, timeStep, comp, nSnaps, kind='recur', tw=None, nPC=1, prepass=True, nTS=1, variant=None,
+               spectra=None):
+    """The emulated srb_integrate on tracks already in the C-ABI layout (host.PackedTracks); `A` are initialised Args
+    with sigma_particle / L_screen set.  Returns (spectra in the DEVICE layout (nSnaps, nPhi, nAxis2, nOmega), accumulated
+    into `spectra` when given like the C ABI does; (passed, visited))."""
+    so = _SO if variant is None else os.path.join(_HERE, f'libsrb_emu_{variant[0]}.so')
+    build(so, () if variant is None else variant[1])
+    lib = ctypes.CDLL(so)
+    L_screen = A.get('L_screen')
+    T = host.grid_tables(A)
     n_w, n_2, n_p = (int(v) for v in A['gridNodeNums'])
     g = _lib.srb_grid()
     g.mode, g.comp = _lib.MODE[A['mode']], _lib.COMP[comp]
@@ -69,7 +81,8 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     t.itStart, t.itEnd, t.itSnaps = pk.itStart.ctypes.data, pk.itEnd.ctypes.data, pk.itSnaps.ctypes.data
     t.itSnapsStride, t.totalSteps_host = pk.snapStride, pk.total
     keys = host.COMP_KEYS[comp]
-    spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
+    if spectra is None:
+        spectra = [np.zeros((nSnaps, n_p, n_2, n_w)) for _ in keys]
     sp = (ctypes.c_void_p * len(keys))(*[s.ctypes.data for s in spectra])
     kind_i = {'direct': 0, 'recur': 1, 'pair': 3, 'pair_fma': 4, 'drec': 5, 'pair_ws': 6}[kind]
     if literal:
@@ -83,5 +96,4 @@ def run(Args, tracks, timeStep, comp='total', L_screen=None, it_range=None, nSna
     rc = lib.srb_emu_integrate(ctypes.byref(g), ctypes.byref(t), sp, len(keys), kind_i, int(tw),
                                ctypes.c_uint32(nPC), cnt, ctypes.c_int(1 if prepass else 0), ctypes.c_uint32(nTS))
     assert rc == 0, 'emulator has no such configuration'
-    rad = {k: np.ascontiguousarray(s.swapaxes(-1, -3)) for k, s in zip(keys, spectra)}
-    return rad, (cnt[0], cnt[1])
+    return spectra, (cnt[0], cnt[1])
