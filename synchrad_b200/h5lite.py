@@ -290,6 +290,11 @@ class _RNode:
         shape = self._rd.dataset_info(self._addr)[2]
         return tuple(int(v) for v in shape) if shape is not None else (0,)
 
+    @property
+    def dtype(self):
+        """Stored element type (h5py: `dset.dtype`)."""
+        return self._rd.dataset_info(self._addr)[0]
+
     def read_direct(self, dest):
         """h5py's `dset.read_direct(dest)`: fill `dest` without an intermediate array."""
         self._rd.read_direct(self._addr, dest)
