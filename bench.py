@@ -23,6 +23,8 @@ Legs of the default run, all in the ONE JSON line:
     fp32 ......... mixed-precision (default float mode) and literal (reference-parity float mode) throughput + rooflines
     e2e_api ...... calculate_spectrum(file_tracks=..., file_spectrum=...) (tutorials/PIC/compute_spectrum.py:16-18) on
                    a bounded sample, host-side seconds broken out
+    e2e_list ..... calculate_spectrum(particleTracks=<Python list of NumPy tracks>) on the whole shard: the reference's
+                   in-memory call signature, packing / upload / kernel pipelined batch by batch
     cpu_baseline . the reference's kernels (g++ -O3, scalar libm, OpenMP) on the host cores, bounded sample
 """
 import argparse
@@ -453,6 +455,39 @@ def run_product(a):
             }
         del tr_list
 
+    # ---------------- list leg: the reference's in-memory call signature (a Python list of per-particle NumPy arrays,
+    # tests/test_undulator_analytic.py:69) on the WHOLE shard: packing into pinned memory, upload and kernel are pipelined
+    # batch by batch inside calculate_spectrum (host.pipelined_batches)
+    e2e_list = None
+    if rank == 0 and world == 1 and a.list_steps > 0:
+        try:
+            tr_all = [[pk.coords[c][i * n_s:(i + 1) * n_s] for c in range(6)] + [1.0] for i in range(n_p)]
+            clist = make_calc(a.dtype, phasor=a.phasor)
+            secs = []
+            for _ in range(a.list_steps + 1):                      # the first call is the warm-up
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                clist.calculate_spectrum(tr_all, timeStep=synthetic.C5_DT, comp='total', verbose=False)
+                torch.cuda.synchronize(dev)
+                secs.append(time.perf_counter() - t0)
+            list_s = sum(secs[1:]) / len(secs[1:])
+            lr = clist.last_run
+            chk = float(clist.Data['radiation']['total'].sum())
+            e2e_list = {
+                'value': updates_rank / list_s, 'unit': 'updates/s', 's_per_call': list_s, 'calls_timed': len(secs) - 1,
+                'path': 'SynchRad(calc_input).calculate_spectrum(particleTracks=<list of [x, y, z, ux, uy, uz, w] NumPy '
+                        'arrays>, timeStep=...) -> host float64 spectrum; the whole shard',
+                'particles': n_p, 'track_steps': n_s, 'pipelined_batches': lr['batches'],
+                'seconds': {'host_pack_total': lr['host_pack_s'], 'gpu_integrate': lr['integrate_ms'] * 1e-3,
+                            'call_total': secs[-1]},
+                'h2d_bytes_per_call': lr['h2d_bytes'], 'd2h_bytes_per_call': lr['d2h_bytes'],
+                'spectrum_checksum': chk,
+                'checksum_rel_diff_vs_e2e': abs(chk - e2e_checksum) / abs(e2e_checksum) if e2e_checksum else None,
+            }
+            del tr_all, clist
+        except Exception as exc:                                   # an auxiliary leg must not cost the headline line
+            e2e_list = {'error': repr(exc)[:400]}
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -533,6 +568,8 @@ def run_product(a):
         line['fp32'] = fp32
     if e2e_api is not None:
         line['e2e_api'] = e2e_api
+    if e2e_list is not None:
+        line['e2e_list'] = e2e_list
     if cpu is not None:
         line['cpu_baseline'] = cpu
     os.write(json_fd, (json.dumps(line) + '\n').encode())
@@ -619,6 +656,7 @@ def main():
                    help='share of the shard the literal-fp32 leg integrates (same recipe, linear in particles)')
     p.add_argument('--api-particles', type=int, default=1250, help='tracks in the file of the e2e_api leg (0 = skip)')
     p.add_argument('--api-steps', type=int, default=2)
+    p.add_argument('--list-steps', type=int, default=1, help='timed calls of the list-of-tracks leg on the whole shard (0 = skip)')
     p.add_argument('--tmpdir', default=None)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-fp32', action='store_true')
