@@ -253,12 +253,26 @@ class SynchRad(Utilities):
                 spans = host.split_batches(lengths, max(int(budget) // 96, 1))
             batches = spans
         res, h2d, upd, ms = None, 0, 0, 0.0
+        done_tracks = []
         # Track sets larger than the device: batch k+1 is packed on the host and uploaded on a second stream while batch
         # k is being integrated (srb_integrate never synchronises; the reference's loop at calc.py:257-267 is serial)
         upload = torch.cuda.Stream(self.device) if len(batches) > 1 else None
         timers = []
+        bar = None
+        if len(batches) > 1 and self.rank == 0 and verbose:
+            try:                                 # the reference walks its per-particle loop under tqdm (calc.py:252-253)
+                from tqdm import tqdm
+                bar = tqdm(total=len(particleTracks))
+            except ImportError:
+                pass
         try:
             for b in batches:
+                if len(timers) >= 2:
+                    # the host runs at most two batches ahead of the device: bounds the tracks in flight on the device (and
+                    # in pinned memory) for sets larger than the device, and keeps the progress bar honest
+                    timers[-2][1].synchronize()
+                    if bar is not None:
+                        bar.update(done_tracks[len(timers) - 2])
                 if isinstance(b, tuple):
                     t0 = time.perf_counter()
                     alloc = engine.PinnedAlloc()
@@ -269,12 +283,17 @@ class SynchRad(Utilities):
                                        spectra=None if res is None else res.spectra,
                                        counters_into=None if res is None else res.counters, upload_stream=upload, **run)
                 timers.append(res.events)
+                done_tracks.append(int(packed.n))
                 h2d += int(sum(a.nbytes for a in packed.coords) + packed.offsets.nbytes + packed.w.nbytes
                            + packed.itStart.nbytes + packed.itEnd.nbytes + packed.itSnaps.nbytes)
                 upd += int(packed.updates_per_node)
             torch.cuda.synchronize(self.device)
             ms = float(sum(e0.elapsed_time(e1) for e0, e1 in timers))
+            if bar is not None:
+                bar.update(sum(done_tracks[max(len(timers) - 2, 0):]))
         finally:
+            if bar is not None:
+                bar.close()
             if track_source is not None:
                 track_source.close()
         if it_range is None and packed.n:

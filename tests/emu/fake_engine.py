@@ -20,6 +20,9 @@ class _Event:
     def elapsed_time(self, other):
         return 0.0
 
+    def synchronize(self):
+        pass
+
 
 def _choose(Args, comp, phasor):
     if phasor not in ('auto', None):

@@ -103,7 +103,7 @@ def test_argument_errors(emulated_device):
         no_device.calculate_spectrum(tracks, timeStep=dt)
 
 
-def test_batches_forced_and_pipelined(emulated_device, oracle, monkeypatch):
+def test_batches_forced_and_pipelined(emulated_device, oracle, monkeypatch, capsys):
     from synchrad_b200 import host
     tracks, dt, args = small(n=9, seed=6)
     n = len(tracks[0][0])
@@ -117,7 +117,12 @@ def test_batches_forced_and_pipelined(emulated_device, oracle, monkeypatch):
     piped = emulated_device(dict(args))
     piped.calculate_spectrum([list(t) for t in tracks], timeStep=dt, comp='cartesian_complex', nSnaps=2, verbose=False)
     assert (one.last_run['batches'], forced.last_run['batches'], piped.last_run['batches']) == (1, 5, 4)
-    for calc in (forced, piped):
+    # verbose: the reference's per-particle tqdm bar, here over the tracks of the finished batches
+    loud = emulated_device(dict(args))
+    loud.calculate_spectrum([list(t) for t in tracks], timeStep=dt, comp='cartesian_complex', nSnaps=2)
+    err = capsys.readouterr().err
+    assert '9/9' in err and loud.last_run['batches'] == 4
+    for calc in (forced, piped, loud):
         close(calc, ref['radiation'])
         assert calc.total_weight == one.total_weight
         assert calc.last_run['passed_updates'] == one.last_run['passed_updates'] == ref['passed']
