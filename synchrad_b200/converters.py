@@ -212,5 +212,12 @@ def tracksFromOPMD_old(*args, **kwargs):
         'converters.py:166-167) and is superseded by tracksFromOPMD')
 
 
+def __getattr__(name):
+    if name in ('record_particles_step', 'record_particles_first'):
+        raise NotImplementedError(f'{name} is a numba helper of tracksFromOPMD_old (converters.py:354-393), which is not '
+                                  'mirrored: use tracksFromOPMD')
+    raise AttributeError(name)
+
+
 __all__ = ['tracksFromOPMD', 'tracksFromOPMD_old', 'tracksFromVSIM', 'split_track_by_nans', 'tracks_from_series',
            'read_tracks', 'get_Larmor']

@@ -127,6 +127,10 @@ def test_reference_import_paths():
     for name in ('tracksFromOPMD', 'tracksFromVSIM', 'split_track_by_nans', 'read_tracks', 'get_Larmor', 'J_in_um'):
         assert callable(getattr(su, name)) or name == 'J_in_um'
     assert sc.tracksFromOPMD is converters.tracksFromOPMD
+    with pytest.raises(NotImplementedError):
+        from synchrad.utils import record_particles_step  # noqa: F401
+    with pytest.raises(ImportError):
+        from synchrad.utils import no_such_name  # noqa: F401
 
 
 def test_converted_file_feeds_the_path(tmp_path):
