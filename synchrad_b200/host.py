@@ -347,7 +347,10 @@ def pipelined_batches(lengths, device_steps, batch_bytes=None):
             cuts = np.searchsorted(cum, total * np.arange(1, n_b) / n_b, side='left') + 1
             cuts = np.unique(np.clip(cuts, 1, len(lengths) - 1)) if len(lengths) > 1 else np.zeros(0, dtype=np.int64)
             edges = [0] + [int(c) for c in cuts] + [len(lengths)]
-            return [(a, b) for a, b in zip(edges, edges[1:]) if b > a]
+            spans = [(a, b) for a, b in zip(edges, edges[1:]) if b > a]
+            bounds = np.concatenate(([0], cum))
+            if all(bounds[b] - bounds[a] <= steps for a, b in spans):    # ragged shares can exceed the average
+                return spans
         steps = min(steps, -(-total // n_b))
     return split_batches(lengths, max(steps, 1))
 

@@ -161,3 +161,93 @@ def test_balanced_partition_covers_every_track_once():
     np.testing.assert_array_equal(host.select_tracks(10, 7, 1, 3), [1, 4])       # reference split unchanged
     with pytest.raises(ValueError):
         host.select_tracks(5, None, 0, 2, [3] * 5, 'nope')
+
+
+def _pack_naive(tracks, weights, it_range, nSnaps):
+    """Track-at-a-time packing as the reference does it (calc.py:579-603, 292-307): the yardstick for pack_tracks."""
+    lens = [int(np.asarray(t[0]).size) for t in tracks]
+    coords = [np.concatenate([np.asarray(t[c], dtype=np.double).reshape(-1) for t in tracks]) if tracks else np.zeros(0)
+              for c in range(6)]
+    if it_range is None:
+        starts, ends = [0] * len(tracks), lens
+        snaps = [host.snap_iterations((0, m), nSnaps) for m in lens]
+    else:
+        starts = [t[7] if len(t) == 8 else 0 for t in tracks]
+        ends = [it_range[-1]] * len(tracks)
+        snaps = host.snap_iterations(it_range, nSnaps)
+    upd = sum(max(0, min(m - 1, e - 1)) for m, e in zip(lens, ends))
+    return lens, coords, starts, ends, snaps, upd
+
+
+def test_pack_tracks_equals_track_at_a_time_packing():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 40), min_size=0, max_size=12), st.integers(1, 4), st.booleans(), st.integers(0, 2 ** 31))
+    def check(lens, nSnaps, with_range, seed):
+        rng = np.random.default_rng(seed)
+        kinds = (np.float64, np.float32, np.int64, list)
+        tracks = []
+        for m in lens:
+            cols = []
+            for c in range(6):
+                a = rng.normal(size=m) * 10
+                k = kinds[int(rng.integers(len(kinds)))]
+                cols.append([float(v) for v in a] if k is list else a.astype(k))
+            t = cols + [float(rng.uniform(0.5, 2))]
+            if rng.integers(2):
+                t.append(int(rng.integers(0, 9)))
+            tracks.append(t)
+        it_range = (1, 30) if with_range else None
+        w = [t[6] for t in tracks]
+        P = host.pack_tracks(tracks, w, np.double, it_range, nSnaps)
+        n = len(tracks)
+        L, coords, starts, ends, snaps, upd = _pack_naive(tracks, w, it_range, nSnaps)
+        assert P.n == n and P.total == sum(L) and list(np.diff(P.offsets[:n + 1])) == L
+        for c in range(6):
+            assert np.array_equal(P.coords[c][:P.total], coords[c])
+        assert list(P.w[:n]) == w and list(P.itStart[:n]) == starts and list(P.itEnd[:n]) == ends
+        if it_range is None:
+            assert P.snapStride == nSnaps and all(np.array_equal(P.itSnaps[i], snaps[i]) for i in range(n))
+        else:
+            assert P.snapStride == 0 and np.array_equal(P.itSnaps, snaps)
+        assert P.updates_per_node == upd
+        # the same tracks, lengths handed in (what calc.py does), and as lazy file-style tracks mixed with lists
+        P2 = host.pack_tracks(tracks, w, np.double, it_range, nSnaps, lengths=L)
+        assert all(np.array_equal(P2.coords[c][:P.total], coords[c]) for c in range(6))
+
+        class Lazy:
+            def __init__(self, t):
+                self.t, self.n = t, int(np.asarray(t[0]).size)
+
+            def __len__(self):
+                return len(self.t)
+
+            def __getitem__(self, k):
+                return self.t[k]
+
+            def read_into(self, c, dest):
+                dest[...] = np.asarray(self.t[c], dtype=np.double)
+        mixed = [Lazy(t) if i % 2 else t for i, t in enumerate(tracks)]
+        P3 = host.pack_tracks(mixed, w, np.double, it_range, nSnaps)
+        assert all(np.array_equal(P3.coords[c][:P.total], coords[c]) for c in range(6))
+        assert list(P3.itStart[:n]) == starts and P3.updates_per_node == upd
+
+    check()
+
+
+def test_pipelined_batches_properties():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(0, 5000), min_size=0, max_size=60), st.integers(1, 200000), st.integers(48, 48 * 20000))
+    def check(lengths, device_steps, batch_bytes):
+        spans = host.pipelined_batches(lengths, device_steps, batch_bytes=batch_bytes)
+        n = len(lengths)
+        assert spans[0][0] == 0 and spans[-1][1] == n                       # every track exactly once, in order
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(b > a for a, b in spans) or n == 0
+        for a, b in spans:                                                  # the device bound holds unless ONE track breaks it
+            assert sum(lengths[a:b]) <= device_steps or b - a == 1
+
+    check()
